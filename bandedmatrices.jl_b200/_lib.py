@@ -1,0 +1,118 @@
+"""ctypes binding of libbmb200.so (include/bmb200.h).  No fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbmb200.so")
+
+i64 = C.c_int64
+dbl = C.c_double
+vp = C.c_void_p
+ch = C.c_char
+
+# name -> (restype, argtypes); mirrors include/bmb200.h one to one
+PROTOTYPES = {
+    "bmb200_version": (C.c_int, []),
+    "bmb200_create": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
+    "bmb200_destroy": (C.c_int, [vp]),
+    "bmb200_set_stream": (C.c_int, [vp, vp]),
+    "bmb200_sync": (C.c_int, [vp]),
+    "bmb200_malloc": (C.c_int, [vp, C.POINTER(vp), C.c_size_t]),
+    "bmb200_free": (C.c_int, [vp, vp]),
+    "bmb200_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "bmb200_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "bmb200_last_error": (C.c_char_p, [vp]),
+    "bmb200_launch_count": (i64, [vp]),
+    "bmb200_dgbmv": (C.c_int, [vp, ch, i64, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
+    "bmb200_dgbmm_bb": (C.c_int, [vp] + [i64] * 9 + [dbl, vp, i64, vp, i64, dbl, vp, i64]),
+    "bmb200_dgbmm_bd": (C.c_int, [vp, ch, i64, i64, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
+    "bmb200_dfill_lmul": (C.c_int, [vp, dbl, vp, i64, i64, i64, i64]),
+    "bmb200_dband_widen": (C.c_int, [vp, i64, i64, i64, vp, i64, vp, i64]),
+    "bmb200_dgbtrf": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(C.c_int)]),
+    "bmb200_dgbtrs": (C.c_int, [vp, ch, i64, i64, i64, i64, vp, i64, vp, vp, i64]),
+    "bmb200_dgbmv_host": (C.c_int, [vp, ch, i64, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
+    "bmb200_dgbsv_host": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, vp, i64, C.POINTER(C.c_int)]),
+    "bmb200_dgbmm_bb_host": (C.c_int, [vp] + [i64] * 9 + [dbl, vp, i64, vp, i64, dbl, vp, i64]),
+    "bmb200_halo_create": (C.c_int, [vp, i64, vp]),
+    "bmb200_halo_connect": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    "bmb200_halo_destroy": (C.c_int, [vp]),
+    "bmb200_dgbmv_sharded": (C.c_int, [vp, i64, i64, i64, i64, i64, dbl, vp, i64, vp, dbl, vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libbmb200.so and attach prototypes.  Raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C bandedmatrices.jl_b200/csrc).  There is no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError here == header/library drift
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class BMB200Error(RuntimeError):
+    pass
+
+
+class Handle:
+    """One handle per (device, stream); owns scratch and the launch counter."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load()
+        self.h = vp()
+        rc = self.lib.bmb200_create(C.byref(self.h), int(device), vp(stream) if stream else None)
+        if rc != 0:
+            raise BMB200Error(f"bmb200_create(device={device}) failed with {rc}: no usable sm_100a GPU (no CPU fallback)")
+        self.device = int(device)
+
+    def check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self.lib.bmb200_last_error(self.h)
+            raise BMB200Error(f"{what} failed: rc={rc} {msg.decode() if msg else ''}")
+
+    def set_stream(self, stream_ptr: int) -> None:
+        self.check(self.lib.bmb200_set_stream(self.h, vp(stream_ptr) if stream_ptr else None), "set_stream")
+
+    def sync(self) -> None:
+        self.check(self.lib.bmb200_sync(self.h), "sync")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.bmb200_launch_count(self.h))
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.bmb200_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_handles: dict = {}
+
+
+def handle(device: int = 0) -> Handle:
+    """Process-wide default handle for ``device``, bound to torch's CURRENT stream at call time."""
+    import torch
+
+    hd = _handles.get(device)
+    if hd is None:
+        hd = _handles[device] = Handle(device)
+    hd.set_stream(torch.cuda.current_stream(device).cuda_stream)
+    return hd

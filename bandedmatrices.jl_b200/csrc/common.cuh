@@ -1,0 +1,95 @@
+// common.cuh -- shared internals of libbmb200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bmb200.h"
+
+typedef int64_t i64;
+
+struct bmb200_halo {
+    // this rank's mailbox (device memory, exported through CUDA IPC):
+    //   [0 .. max_halo)            x entries pushed by the LEFT neighbour  (its last kl entries)
+    //   [max_halo .. 2*max_halo)   x entries pushed by the RIGHT neighbour (its first ku entries)
+    //   flags: 2 x uint64 epoch counters at the end
+    double *box = nullptr;
+    double *left_box = nullptr;   // peer mapping of the left neighbour's mailbox
+    double *right_box = nullptr;  // peer mapping of the right neighbour's mailbox
+    i64 max_halo = 0;
+    int rank = 0, nranks = 1;
+    unsigned long long epoch = 0;
+};
+
+struct bmb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int64_t launches = 0;
+    char err[256] = {0};
+    // small persistent device scratch (LU bookkeeping, info words)
+    int *d_info = nullptr;     // [0]=info, [1]=ju, spare
+    void *scratch = nullptr;   // grow-only workspace
+    size_t scratch_bytes = 0;
+    // pinned staging + second stream for the host-buffer entry points
+    void *pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bmb200_halo halo;
+};
+
+#define BMB_CUDA(h, call)                                                                   \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            snprintf((h)->err, sizeof((h)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e_));                                               \
+            return BMB200_ERR_CUDA - (int)e_;                                               \
+        }                                                                                   \
+    } while (0)
+
+#define BMB_LAUNCH_CHECK(h)          \
+    do {                             \
+        (h)->launches++;             \
+        BMB_CUDA(h, cudaGetLastError()); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int bmb_ensure_scratch(bmb200_ctx *h, size_t bytes);
+
+static inline i64 imin64(i64 a, i64 b) { return a < b ? a : b; }
+static inline i64 imax64(i64 a, i64 b) { return a > b ? a : b; }
+static inline i64 cdiv64(i64 a, i64 b) { return (a + b - 1) / b; }
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ double ld_stream(const double *p) {  // read-once data: bypass L1 allocation
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void ld_stream_v2(const double *p, double &a, double &b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+__device__ __forceinline__ void ld_stream_v4(const double *p, double &a, double &b, double &c, double &d) {
+    // 256-bit global load (LDG.E.256, sm_100+)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(a), "=d"(b), "=d"(c), "=d"(d)
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_stream(double *p, double v) {
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }

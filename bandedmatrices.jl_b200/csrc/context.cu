@@ -1,0 +1,175 @@
+// context.cu -- handle, memory and small utility kernels of libbmb200.
+#include "common.cuh"
+
+extern "C" int bmb200_version(void) { return BMB200_VERSION; }
+
+extern "C" int bmb200_create(bmb200_handle_t *out, int device, void *stream)
+{
+    if (!out) return -1;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        fprintf(stderr, "libbmb200: no CUDA device available -- there is no CPU fallback\n");
+        return BMB200_ERR_CUDA - (int)cudaErrorNoDevice;
+    }
+    if (device < 0 || device >= count) return -2;
+    bmb200_ctx *h = new bmb200_ctx();
+    h->device = device;
+    h->stream = (cudaStream_t)stream;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return BMB200_ERR_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        fprintf(stderr, "libbmb200: device %d is sm_%d%d; this library is built for sm_100a only\n", device,
+                prop.major, prop.minor);
+        delete h;
+        return BMB200_ERR_CUDA - (int)cudaErrorInvalidDevice;
+    }
+    if (cudaMalloc(&h->d_info, 64 * sizeof(int)) != cudaSuccess) { delete h; return BMB200_ERR_CUDA; }
+    cudaMemset(h->d_info, 0, 64 * sizeof(int));
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+    *out = h;
+    return 0;
+}
+
+extern "C" int bmb200_destroy(bmb200_handle_t h)
+{
+    if (!h) return -1;
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    bmb200_halo_destroy(h);
+    if (h->d_info) cudaFree(h->d_info);
+    if (h->scratch) cudaFree(h->scratch);
+    for (int i = 0; i < 2; ++i)
+        if (h->pinned[i]) cudaFreeHost(h->pinned[i]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 4; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return 0;
+}
+
+extern "C" int bmb200_set_stream(bmb200_handle_t h, void *stream)
+{
+    if (!h) return -1;
+    h->stream = (cudaStream_t)stream;
+    return 0;
+}
+
+extern "C" int bmb200_sync(bmb200_handle_t h)
+{
+    if (!h) return -1;
+    DeviceGuard g(h->device);
+    BMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bmb200_malloc(bmb200_handle_t h, void **dptr, size_t bytes)
+{
+    if (!h) return -1;
+    if (!dptr) return -2;
+    DeviceGuard g(h->device);
+    BMB_CUDA(h, cudaMalloc(dptr, bytes ? bytes : 1));
+    return 0;
+}
+
+extern "C" int bmb200_free(bmb200_handle_t h, void *dptr)
+{
+    if (!h) return -1;
+    DeviceGuard g(h->device);
+    BMB_CUDA(h, cudaFree(dptr));
+    return 0;
+}
+
+extern "C" int bmb200_memcpy_h2d(bmb200_handle_t h, void *dst, const void *hsrc, size_t bytes)
+{
+    if (!h) return -1;
+    DeviceGuard g(h->device);
+    BMB_CUDA(h, cudaMemcpyAsync(dst, hsrc, bytes, cudaMemcpyHostToDevice, h->stream));
+    BMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int bmb200_memcpy_d2h(bmb200_handle_t h, void *hdst, const void *dsrc, size_t bytes)
+{
+    if (!h) return -1;
+    DeviceGuard g(h->device);
+    BMB_CUDA(h, cudaMemcpyAsync(hdst, dsrc, bytes, cudaMemcpyDeviceToHost, h->stream));
+    BMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" const char *bmb200_last_error(bmb200_handle_t h) { return h ? h->err : "null handle"; }
+extern "C" int64_t bmb200_launch_count(bmb200_handle_t h) { return h ? h->launches : -1; }
+
+int bmb_ensure_scratch(bmb200_ctx *h, size_t bytes)
+{
+    if (bytes <= h->scratch_bytes) return 0;
+    if (h->scratch) {
+        BMB_CUDA(h, cudaStreamSynchronize(h->stream));
+        BMB_CUDA(h, cudaFree(h->scratch));
+        h->scratch = nullptr;
+        h->scratch_bytes = 0;
+    }
+    BMB_CUDA(h, cudaMalloc(&h->scratch, bytes));
+    h->scratch_bytes = bytes;
+    return 0;
+}
+
+// ---- C <- beta*C (beta == 0 zero-fills): _fill_lmul! / _fill_rmul!, src/generic/utils.jl:29-31 ----
+__global__ void fill_lmul_kernel(double beta, double *__restrict__ c, i64 rows, i64 cols, i64 ldc, i64 inc)
+{
+    i64 total = rows * cols;
+    for (i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        i64 j = t / rows, i = t - j * rows;
+        double *p = c + i * inc + j * ldc;
+        *p = (beta == 0.0) ? 0.0 : __dmul_rn(beta, *p);
+    }
+}
+
+extern "C" int bmb200_dfill_lmul(bmb200_handle_t h, double beta, double *dC, int64_t rows, int64_t cols,
+                                 int64_t ldc, int64_t inc)
+{
+    if (!h) return -1;
+    if (rows < 0) return -4;
+    if (cols < 0) return -5;
+    if (rows == 0 || cols == 0 || beta == 1.0) return 0;
+    if (!dC) return -3;
+    DeviceGuard g(h->device);
+    i64 total = rows * cols;
+    int blocks = (int)imin64(cdiv64(total, 256), (i64)h->sm_count * 16);
+    fill_lmul_kernel<<<blocks, 256, 0, h->stream>>>(beta, dC, rows, cols, ldc, inc);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
+// ---- widening copy for lu(A): BandedMatrix{T}(A,(l,l+u)), src/banded/BandedLU.jl:110 --------------
+__global__ void band_widen_kernel(i64 n, i64 l, i64 rows_src, const double *__restrict__ a, i64 lda,
+                                  double *__restrict__ ab, i64 ldab)
+{
+    i64 rows_dst = rows_src + l;
+    i64 total = rows_dst * n;
+    for (i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        i64 j = t / rows_dst, r = t - j * rows_dst;
+        ab[r + j * ldab] = (r < l) ? 0.0 : a[(r - l) + j * lda];
+    }
+}
+
+extern "C" int bmb200_dband_widen(bmb200_handle_t h, int64_t n, int64_t l, int64_t u, const double *dA,
+                                  int64_t lda, double *dAB, int64_t ldab)
+{
+    if (!h) return -1;
+    if (n < 0) return -2;
+    if (l < 0) return -3;
+    if (l + u + 1 < 0) return -4;
+    if (lda < l + u + 1) return -6;
+    if (ldab < 2 * l + u + 1) return -8;
+    if (n == 0) return 0;
+    DeviceGuard g(h->device);
+    i64 total = (2 * l + u + 1) * n;
+    int blocks = (int)imin64(cdiv64(total, 256), (i64)h->sm_count * 16);
+    band_widen_kernel<<<blocks, 256, 0, h->stream>>>(n, l, l + u + 1, dA, lda, dAB, ldab);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}

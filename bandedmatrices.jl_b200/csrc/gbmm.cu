@@ -1,0 +1,195 @@
+// gbmm.cu -- banded x banded and banded x dense products on sm_100a.
+//
+// bmb200_dgbmm_bb replaces _gbmm! (src/banded/gbmm.jl:296-340): the reference issues ONE dgbmv_ per
+// column of C (m BLAS calls, three regimes + a trailing beta fill); here one launch computes
+//     C[k,j] = beta*C[k,j] (or 0) then, for nu ascending over band(A row k) ^ band(B col j),
+//              C[k,j] = fma(alpha*B[nu,j], A[k,nu], C[k,j])
+// which is exactly the per-element operation order of that dgbmv_ sequence, so the
+// result is bit-identical to the reference CPU path.
+// bmb200_dgbmm_bd replaces the per-column mul! loop of src/generic/matmul.jl:243-256.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// v1 banded x banded: warp = output column, lanes = rows of that column (contiguous in C and in
+// every A column), sweep over nu.  A is re-read from L1/L2 (each A column serves Bl+Bu+1 output
+// columns).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gbmm_bb_sweep(i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 Cu, double alpha,
+              const double *__restrict__ a, i64 lda, const double *__restrict__ b, i64 ldb, double beta,
+              double *__restrict__ c, i64 ldc)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 j = warp; j < m; j += nwarps) {
+        i64 k0 = j - Cu; if (k0 < 0) k0 = 0;
+        i64 k1 = j + Cl; if (k1 > n - 1) k1 = n - 1;
+        i64 v0 = j - Bu; if (v0 < 0) v0 = 0;
+        i64 v1 = j + Bl; if (v1 > nu - 1) v1 = nu - 1;
+        const double *bcol = b + j * ldb + (Bu - j);   // B[v,j] = bcol[v]
+        double *ccol = c + j * ldc + (Cu - j);         // C[k,j] = ccol[k]
+        for (i64 kb = k0; kb <= k1; kb += 32) {
+            const i64 k = kb + lane;
+            const bool live = k <= k1;
+            double acc = (beta == 0.0 || !live) ? 0.0 : __dmul_rn(beta, ccol[k]);
+            if (alpha != 0.0) {
+                // only nu with band(A col nu) touching rows [kb, kb+31]
+                i64 w0 = kb - Al; if (w0 < v0) w0 = v0;
+                i64 w1 = kb + 31 + Au; if (w1 > v1) w1 = v1;
+#pragma unroll 4
+                for (i64 v = w0; v <= w1; ++v) {
+                    const double t = __dmul_rn(alpha, bcol[v]);
+                    if (live && k >= v - Au && k <= v + Al) acc = fma(t, a[(Au + k - v) + v * lda], acc);
+                }
+            }
+            if (live) ccol[k] = acc;
+        }
+    }
+}
+
+extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t m, int64_t Al, int64_t Au,
+                               int64_t Bl, int64_t Bu, int64_t Cl, int64_t Cu, double alpha, const double *dA,
+                               int64_t lda, const double *dB, int64_t ldb, double beta, double *dC, int64_t ldc)
+{
+    if (!h) return -1;
+    if (n < 0) return -2;
+    if (nu < 0) return -3;
+    if (m < 0) return -4;
+    if (Al < 0) return -5;
+    if (Au < 0) return -6;
+    if (Bl < 0) return -7;
+    if (Bu < 0) return -8;
+    if (Cl < 0 || Cl > Al + Bl) return -9;
+    if (Cu < 0 || Cu > Au + Bu) return -10;
+    if (lda < Al + Au + 1) return -13;
+    if (ldb < Bl + Bu + 1) return -15;
+    if (ldc < Cl + Cu + 1) return -18;
+    if (n == 0 || m == 0) return 0;
+    if (!dC || (nu > 0 && (!dA || !dB))) return -12;
+    DeviceGuard g(h->device);
+    const int threads = 256;
+    const i64 blocks = imin64(cdiv64(m, threads / 32), (i64)h->sm_count * 8);
+    gbmm_bb_sweep<<<(unsigned)blocks, threads, 0, h->stream>>>(n, nu, m, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB,
+                                                               ldb, beta, dC, ldc);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// banded x dense ('N'): lane = row, NR right-hand sides per thread share every A load.
+// ------------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(256)
+gbmm_bd_n(i64 m, i64 n, i64 kl, i64 ku, i64 nrhs, double alpha, const double *__restrict__ a, i64 lda,
+          const double *__restrict__ b, i64 ldb, double beta, double *__restrict__ c, i64 ldc, i64 row_tiles)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const i64 rhs_tiles = (nrhs + NR - 1) / NR;
+    const i64 total = row_tiles * rhs_tiles;
+    for (i64 w = warp; w < total; w += nwarps) {
+        const i64 rt = w % row_tiles, ct = w / row_tiles;
+        const i64 i = rt * 32 + lane, c0 = ct * NR;
+        const bool live = i < m;
+        double acc[NR];
+#pragma unroll
+        for (int q = 0; q < NR; ++q)
+            acc[q] = (beta == 0.0 || !live || c0 + q >= nrhs) ? 0.0 : __dmul_rn(beta, c[i + (c0 + q) * ldc]);
+        i64 jlo = rt * 32 - kl; if (jlo < 0) jlo = 0;
+        i64 jhi = rt * 32 + 31 + ku; if (jhi > n - 1) jhi = n - 1;
+        if (alpha != 0.0)
+            for (i64 j = jlo; j <= jhi; ++j) {
+                const bool in = live && i >= j - ku && i <= j + kl;
+                const double av = in ? a[(ku + i - j) + j * lda] : 0.0;
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                    if (c0 + q < nrhs) {
+                        const double t = __dmul_rn(alpha, b[j + (c0 + q) * ldb]);
+                        if (in) acc[q] = fma(t, av, acc[q]);
+                    }
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < NR; ++q)
+            if (live && c0 + q < nrhs) c[i + (c0 + q) * ldc] = acc[q];
+    }
+}
+
+// banded^T x dense: warp = output row j (column of A), shuffle reduction per right-hand side.
+template <int NR>
+__global__ void __launch_bounds__(256)
+gbmm_bd_t(i64 m, i64 n, i64 kl, i64 ku, i64 nrhs, double alpha, const double *__restrict__ a, i64 lda,
+          const double *__restrict__ b, i64 ldb, double beta, double *__restrict__ c, i64 ldc)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const i64 rhs_tiles = (nrhs + NR - 1) / NR;
+    const i64 total = n * rhs_tiles;
+    for (i64 w = warp; w < total; w += nwarps) {
+        const i64 j = w % n, c0 = (w / n) * NR;
+        i64 i0 = j - ku; if (i0 < 0) i0 = 0;
+        i64 i1 = j + kl; if (i1 > m - 1) i1 = m - 1;
+        const double *colp = a + j * lda + (ku - j);
+        double temp[NR];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) temp[q] = 0.0;
+        for (i64 i = i0 + lane; i <= i1; i += 32) {
+            const double av = colp[i];
+#pragma unroll
+            for (int q = 0; q < NR; ++q)
+                if (c0 + q < nrhs) temp[q] = fma(av, b[i + (c0 + q) * ldb], temp[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) temp[q] += __shfl_xor_sync(0xffffffffu, temp[q], o);
+            if (lane == 0 && c0 + q < nrhs) {
+                double *p = c + j + (c0 + q) * ldc;
+                const double y0 = (beta == 0.0) ? 0.0 : __dmul_rn(beta, *p);
+                *p = fma(alpha, temp[q], y0);
+            }
+        }
+    }
+}
+
+extern "C" int bmb200_dgbmm_bd(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
+                               int64_t nrhs, double alpha, const double *dA, int64_t lda, const double *dB,
+                               int64_t ldb, double beta, double *dC, int64_t ldc)
+{
+    if (!h) return -1;
+    const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
+    if (!tr && !(trans == 'N' || trans == 'n')) return -2;
+    if (m < 0) return -3;
+    if (n < 0) return -4;
+    if (kl < 0) return -5;
+    if (ku < 0) return -6;
+    if (nrhs < 0) return -7;
+    if (lda < kl + ku + 1) return -10;
+    const i64 rowsB = tr ? m : n, rowsC = tr ? n : m;
+    if (ldb < imax64(1, rowsB)) return -12;
+    if (ldc < imax64(1, rowsC)) return -15;
+    if (rowsC == 0 || nrhs == 0) return 0;
+    DeviceGuard g(h->device);
+    if (rowsB == 0 || alpha == 0.0) return bmb200_dfill_lmul(h, beta, dC, rowsC, nrhs, ldc, 1);
+    const i64 kle = imin64(kl, m - 1), kue = imin64(ku, n - 1);
+    const double *ae = dA + (ku - kue);
+    const int threads = 256;
+    constexpr int NR = 8;
+    if (!tr) {
+        const i64 row_tiles = cdiv64(m, 32);
+        const i64 total = row_tiles * cdiv64(nrhs, NR);
+        const i64 blocks = imin64(cdiv64(total, threads / 32), (i64)h->sm_count * 8);
+        gbmm_bd_n<NR><<<(unsigned)blocks, threads, 0, h->stream>>>(m, n, kle, kue, nrhs, alpha, ae, lda, dB, ldb, beta,
+                                                                   dC, ldc, row_tiles);
+    } else {
+        const i64 total = n * cdiv64(nrhs, NR);
+        const i64 blocks = imin64(cdiv64(total, threads / 32), (i64)h->sm_count * 8);
+        gbmm_bd_t<NR><<<(unsigned)blocks, threads, 0, h->stream>>>(m, n, kle, kue, nrhs, alpha, ae, lda, dB, ldb, beta,
+                                                                   dC, ldc);
+    }
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}

@@ -1,0 +1,512 @@
+"""Host-side mirror of the reference's hot-path drivers (``mul!`` / ``*`` / ``lu`` / ``ldiv!`` / ``\\``).
+
+Julia is not available in this image, so the driver logic that sits above the native calls
+is restated here in Python over the C ABI -- same names, argument meaning and error
+behaviour as the reference, so that the parity tests read like the reference's own:
+
+=====================================  ===========================================================
+here                                   reference
+=====================================  ===========================================================
+``mul_(y, A, x, alpha, beta)``         ``mul!(y,A,x,α,β)`` -> ``_banded_muladd!`` src/generic/matmul.jl:41-64, 66-92
+``mul_(C, A, B, alpha, beta)``         banded x banded ``gbmm!`` src/banded/gbmm.jl:207-293; banded x dense
+                                       src/generic/matmul.jl:243-256; dense x banded :258-271
+``matmul(A, B)``                       ``A*B`` (``similar(::MulAdd)`` src/generic/matmul.jl:1-6)
+``lu(A)`` / ``lu_(A)``                 ``lu`` / ``lu!`` src/banded/BandedLU.jl:90-111
+``ldiv_(F, B)`` / ``solve(A, b)``      ``ldiv!`` / ``\\`` src/banded/linalg.jl:5-9, 24-30, 41-47
+=====================================  ===========================================================
+
+Every arithmetic step is a kernel of ``libbmb200.so``; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .banded import (BandedMatrix, BandError, DimensionMismatch, LAPACKException, Transposed, bandwidths, colmajor)
+
+vp = C.c_void_p
+
+
+def _h(t: torch.Tensor) -> _lib.Handle:
+    if not t.is_cuda:
+        raise TypeError("operands must live on the GPU (no CPU fallback)")
+    return _lib.handle(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _inc(v: torch.Tensor) -> int:
+    return int(v.stride(0)) if v.shape[0] > 1 else 1
+
+
+def _ld(X: torch.Tensor) -> int:
+    """Leading dimension of a column-major 2-D tensor (stride (1, ld))."""
+    if X.shape[0] > 1 and X.stride(0) != 1:
+        raise TypeError("dense matrices must be column-major (use colmajor()/to_colmajor())")
+    return int(X.stride(1)) if X.shape[1] > 1 else max(1, int(X.shape[0]))
+
+
+# ---------------------------------------------------------------------------------------------
+# _fill_lmul! / _fill_rmul!  (src/generic/utils.jl:29-31): beta == 0 zero-fills (unless Czero)
+# ---------------------------------------------------------------------------------------------
+def _fill_vec(y: torch.Tensor, beta: float, yzero: bool = False) -> None:
+    if y.numel() == 0 or (beta == 0 and yzero):
+        return
+    hd = _h(y)
+    hd.check(hd.lib.bmb200_dfill_lmul(hd.h, float(beta), vp(y.data_ptr()), y.shape[0], 1, 0, _inc(y)), "dfill_lmul")
+
+
+def _fill_cm(X: torch.Tensor, beta: float, zero: bool = False) -> None:
+    """Column-major dense block (rows x cols, stride (1, ld))."""
+    if X.numel() == 0 or (beta == 0 and zero):
+        return
+    hd = _h(X)
+    hd.check(hd.lib.bmb200_dfill_lmul(hd.h, float(beta), vp(X.data_ptr()), X.shape[0], X.shape[1], _ld(X), 1),
+             "dfill_lmul")
+
+
+def _fill_banddata(data: torch.Tensor, beta: float, zero: bool = False) -> None:
+    """Band-data block ``data[c0:c1, r0:r1]`` (tensor layout (n, rows), stride (lda, 1))."""
+    if data.numel() == 0 or (beta == 0 and zero):
+        return
+    hd = _h(data)
+    lda = int(data.stride(0)) if data.shape[0] > 1 else max(1, int(data.shape[1]))
+    hd.check(hd.lib.bmb200_dfill_lmul(hd.h, float(beta), vp(data.data_ptr()), data.shape[1], data.shape[0], lda, 1),
+             "dfill_lmul")
+
+
+def _fill_banded_rows(Cm: BandedMatrix, r0: int, r1: int, c0: int, c1: int, beta: float, zero: bool) -> None:
+    """lmul!(beta, view(C, r0+1:r1, c0+1:c1)) on a BandedMatrix: scale/zero the in-band entries of that block."""
+    if r1 <= r0 or c1 <= c0 or Cm.data.numel() == 0 or (beta == 0 and zero):
+        return
+    rows = Cm.data.shape[1]
+    j = torch.arange(c0, c1, device=Cm.data.device).unsqueeze(1)
+    r = torch.arange(rows, device=Cm.data.device).unsqueeze(0)
+    k = j + r - Cm.u
+    mask = (k >= r0) & (k < r1)
+    blk = Cm.data[c0:c1]
+    if beta == 0:
+        blk[mask] = 0.0
+    else:
+        blk[mask] = blk[mask] * beta
+
+
+# ---------------------------------------------------------------------------------------------
+# matrix * vector
+# ---------------------------------------------------------------------------------------------
+def _banded_gbmv(tA: str, alpha, A: BandedMatrix, x: torch.Tensor, beta, y: torch.Tensor, yzero=False):
+    """_banded_gbmv! + banded_gbmv!  (src/generic/matmul.jl:21-39).  A has non-negative bandwidths here."""
+    if y.shape[0] == 0:
+        return y
+    if x.shape[0] == 0:
+        _fill_vec(y, beta, yzero)
+        return y
+    # Base.unalias(y, x): the reference copies x when it shares memory with y (matmul.jl:35)
+    if x.untyped_storage().data_ptr() == y.untyped_storage().data_ptr():
+        x = x.clone()
+    hd = _h(y)
+    hd.check(hd.lib.bmb200_dgbmv(hd.h, tA.encode(), A.m, A.n, A.l, A.u, float(alpha), vp(A.ptr), A.lda,
+                                 vp(x.data_ptr()), _inc(x), float(beta), vp(y.data_ptr()), _inc(y)), "dgbmv")
+    return y
+
+
+def _banded_muladd_vec(alpha, A: BandedMatrix, x, beta, y, yzero=False):
+    """_banded_muladd!(α,A,x,β,y)  (src/generic/matmul.jl:41-59)."""
+    m, n = A.shape
+    l, u = A.l, A.u
+    if -l > u:
+        _fill_vec(y, beta, yzero)
+    elif l < 0:
+        _banded_gbmv("N", alpha, A.view_cols(-l), x[-l:], beta, y, yzero)
+    elif u < 0:
+        _fill_vec(y[:-u], beta, yzero)
+        _banded_gbmv("N", alpha, A.view_rows(-u), x, beta, y[-u:], yzero)
+    else:
+        _banded_gbmv("N", alpha, A, x, beta, y, yzero)
+    return y
+
+
+def _banded_muladd_row(alpha, At: BandedMatrix, x, beta, y, yzero=False):
+    """_banded_muladd_row!('T', α, transpose(A), x, β, y)  (src/generic/matmul.jl:66-86).
+    ``At`` is the PARENT (column-major) matrix of the transposed operand: y <- α At' x + β y."""
+    n, m = At.shape
+    u, l = At.l, At.u  # reference: u, l = bandwidths(At)
+    if -l > u:
+        _fill_vec(y, beta, yzero)
+    elif l < 0:
+        _banded_gbmv("T", alpha, At.view_rows(-l), x[-l:], beta, y, yzero)
+    elif u < 0:
+        _fill_vec(y[:-u], beta, yzero)
+        _banded_gbmv("T", alpha, At.view_cols(-u), x, beta, y[-u:], yzero)
+    else:
+        _banded_gbmv("T", alpha, At, x, beta, y, yzero)
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
+# banded * banded : gbmm!  (src/banded/gbmm.jl:207-293)
+# ---------------------------------------------------------------------------------------------
+def _num_zeroband_u(A: BandedMatrix) -> int:
+    """gbmm.jl:191-197: number of leading all-zero upper bands (data rows from the top)."""
+    for b in range(A.l + A.u + 1):
+        off = A.u - b
+        js = slice(max(0, off), max(0, min(A.n, A.m + off)))
+        if bool((A.data[js, b] != 0).any()):
+            return b
+    return A.l + A.u + 1
+
+
+def _num_zeroband_l(A: BandedMatrix) -> int:
+    """gbmm.jl:199-205: number of trailing all-zero lower bands (data rows from the bottom)."""
+    rows = A.l + A.u + 1
+    for b in range(rows):
+        r = rows - 1 - b
+        off = A.u - r
+        js = slice(max(0, off), max(0, min(A.n, A.m + off)))
+        if bool((A.data[js, r] != 0).any()):
+            return b
+    return rows
+
+
+def gbmm_(alpha, A: BandedMatrix, B: BandedMatrix, beta, Cm: BandedMatrix, Czero: bool = False):
+    """gbmm!('N','N',α,A,B,β,C)  -- src/banded/gbmm.jl:207-293, branch for branch."""
+    n, nu = A.shape
+    m = B.n
+    Am, An = A.shape
+    Bm, Bn = B.shape
+    assert n == Cm.m and nu == B.m and m == Cm.n
+    if n == 0 or m == 0:
+        return Cm
+    Al, Au = A.l, A.u
+    Bl, Bu = B.l, B.u
+    Ctl, Ctu = Cm.l, Cm.u
+    Cl, Cu = min(n - 1, Al + Bl), min(m - 1, Au + Bu)
+
+    if (-Al > Au) or (-Bl > Bu):  # :231-233  A or B has no bands
+        if not Czero:
+            Cm.data.zero_()
+        return Cm
+    if Al < 0:  # :234-237
+        _fill_banded_rows(Cm, max(1, Bn + Al - 1) - 1, Am, 0, m, beta, Czero)
+        return gbmm_(alpha, A.view_cols(-Al), B.view_rows(-Al), beta, Cm, Czero)
+    if Au < 0:  # :238-241
+        _fill_banded_rows(Cm, 0, -Au, 0, m, beta, Czero)
+        return_c = gbmm_(alpha, A.view_rows(-Au), B, beta, Cm.view_rows(-Au), Czero)
+        del return_c
+        return Cm
+    if Bl < 0:  # :242-245
+        _fill_banded_rows(Cm, 0, n, 0, -Bl, beta, Czero)
+        gbmm_(alpha, A, B.view_cols(-Bl), beta, Cm.view_cols(-Bl), Czero)
+        return Cm
+    if Bu < 0:  # :246-249
+        _fill_banded_rows(Cm, 0, n, max(1, Am + Bu - 1) - 1, Bn, beta, Czero)
+        return gbmm_(alpha, A.view_cols(-Bu), B.view_rows(-Bu), beta, Cm, Czero)
+    if Ctu < Cu:  # :250-264  C has too few upper bands
+        Au_r, Bu_r = _num_zeroband_u(A), _num_zeroband_u(B)
+        if not Ctu >= Cu - Au_r - Bu_r:
+            raise BandError(Cm, Cu - Au_r - Bu_r)
+        if Au - Au_r < -Al or Bu - Bu_r < -Bl:
+            _fill_banddata(Cm.data, beta, Czero)
+            return Cm
+        At = BandedMatrix(A.data[:, Au_r:], n, Al, Au - Au_r)
+        Bt = BandedMatrix(B.data[:, Bu_r:], nu, Bl, Bu - Bu_r)
+        return gbmm_(alpha, At, Bt, beta, Cm, Czero)
+    if Ctl < Cl:  # :265-280  too few lower bands
+        Al_r, Bl_r = _num_zeroband_l(A), _num_zeroband_l(B)
+        if not Ctl >= Cl - Al_r - Bl_r:
+            raise BandError(Cm, Cl - Al_r - Bl_r)
+        if Al - Al_r < -Au or Bl - Bl_r < -Bu:
+            _fill_banddata(Cm.data, beta, Czero)
+            return Cm
+        At = BandedMatrix(A.data[:, : A.data.shape[1] - Al_r], n, Al - Al_r, Au)
+        Bt = BandedMatrix(B.data[:, : B.data.shape[1] - Bl_r], nu, Bl - Bl_r, Bu)
+        return gbmm_(alpha, At, Bt, beta, Cm, Czero)
+
+    # :282-290  scale the extra bands of C, then hand the written band window to _gbmm!
+    rowsC = Cm.data.shape[1]
+    _fill_banddata(Cm.data[:, : min(Ctu - Cu, rowsC)], beta, Czero)
+    _fill_banddata(Cm.data[:, Ctu + Cl + 1 :], beta, Czero)
+    C_data = Cm.data[:, Ctu - Cu : Ctu + Cl + 1]
+    _gbmm(alpha, A, B, beta, C_data, (n, nu, m), (Al, Au), (Bl, Bu), (Cl, Cu), Cm.lda)
+    return Cm
+
+
+def _gbmm(alpha, A, B, beta, C_data, sizes, Ab, Bb, Cb, ldc):
+    """_gbmm!  (src/banded/gbmm.jl:296-340): one bmb200_dgbmm_bb launch instead of m dgbmv_ calls."""
+    n, nu, m = sizes
+    hd = _h(C_data)
+    hd.check(hd.lib.bmb200_dgbmm_bb(hd.h, n, nu, m, Ab[0], Ab[1], Bb[0], Bb[1], Cb[0], Cb[1], float(alpha),
+                                    vp(A.ptr), A.lda, vp(B.ptr), B.lda, float(beta), vp(C_data.data_ptr()), ldc),
+             "dgbmm_bb")
+
+
+# ---------------------------------------------------------------------------------------------
+# banded * dense, dense * banded  (src/generic/matmul.jl:243-271)
+# ---------------------------------------------------------------------------------------------
+def _gbmm_bd(trans, alpha, A: BandedMatrix, B, beta, Cd):
+    hd = _h(Cd)
+    hd.check(hd.lib.bmb200_dgbmm_bd(hd.h, trans.encode(), A.m, A.n, A.l, A.u, Cd.shape[1], float(alpha), vp(A.ptr),
+                                    A.lda, vp(B.data_ptr()), _ld(B), float(beta), vp(Cd.data_ptr()), _ld(Cd)),
+             "dgbmm_bd")
+
+
+def _banded_times_dense(alpha, A, B, beta, Cd):
+    """materialize!(MatMulMatAdd{BandedColumns,Strided,Strided}) matmul.jl:243-256: the reference loops
+    mul!(colC, A, colB, α, β) over columns; all columns go through one multi-RHS launch here, with the
+    same negative-bandwidth re-viewing as _banded_muladd! (matmul.jl:41-59)."""
+    if alpha == 0:
+        _fill_cm(Cd, beta)
+        return Cd
+    tr = isinstance(A, Transposed)
+    P = A.parent if tr else A
+    if Cd.shape[0] == 0 or Cd.shape[1] == 0:
+        return Cd
+    if B.shape[0] == 0:
+        _fill_cm(Cd, beta)
+        return Cd
+    if not tr:
+        l, u = P.l, P.u
+        if -l > u:
+            _fill_cm(Cd, beta)
+        elif l < 0:
+            _gbmm_bd("N", alpha, P.view_cols(-l), B[-l:], beta, Cd)
+        elif u < 0:
+            _fill_cm(Cd[:-u], beta)
+            _gbmm_bd("N", alpha, P.view_rows(-u), B, beta, Cd[-u:])
+        else:
+            _gbmm_bd("N", alpha, P, B, beta, Cd)
+    else:
+        u, l = P.l, P.u
+        if -l > u:
+            _fill_cm(Cd, beta)
+        elif l < 0:
+            _gbmm_bd("T", alpha, P.view_rows(-l), B[-l:], beta, Cd)
+        elif u < 0:
+            _fill_cm(Cd[:-u], beta)
+            _gbmm_bd("T", alpha, P.view_cols(-u), B, beta, Cd[-u:])
+        else:
+            _gbmm_bd("T", alpha, P, B, beta, Cd)
+    return Cd
+
+
+def _dense_times_banded(alpha, Ad, B, beta, Cd):
+    """matmul.jl:258-271: for each row, mul!(rowC, transpose(B), rowA, α, β) (strided x and y)."""
+    if alpha == 0:
+        _fill_cm(Cd, beta)
+        return Cd
+    for i in range(Cd.shape[0]):
+        if isinstance(B, Transposed):
+            _banded_muladd_vec(alpha, B.parent, Ad[i], beta, Cd[i])
+        else:
+            _banded_muladd_row(alpha, B, Ad[i], beta, Cd[i])
+    return Cd
+
+
+# ---------------------------------------------------------------------------------------------
+# public: mul!, *
+# ---------------------------------------------------------------------------------------------
+def _shape(X):
+    return tuple(X.shape)
+
+
+def mul_(Cout, A, B, alpha=1.0, beta=0.0):
+    """``mul!(C, A, B, α, β)``: C <- α A B + β C, dispatching like the reference's MulAdd layouts."""
+    sa, sb, sc = _shape(A), _shape(B), _shape(Cout)
+    if len(sb) == 1:  # matrix * vector (checkdimensions: DimensionMismatch)
+        if sa[1] != sb[0] or sa[0] != sc[0] or len(sc) != 1:
+            raise DimensionMismatch(f"A has dimensions {sa} but B has dimensions {sb} and C {sc}")
+        if isinstance(A, Transposed):
+            return _banded_muladd_row(alpha, A.parent, B, beta, Cout)
+        return _banded_muladd_vec(alpha, A, B, beta, Cout)
+    if sa[1] != sb[0] or sc != (sa[0], sb[1]):
+        raise DimensionMismatch(f"A has dimensions {sa} but B has dimensions {sb} and C {sc}")
+    a_b = isinstance(A, (BandedMatrix, Transposed))
+    b_b = isinstance(B, (BandedMatrix, Transposed))
+    if a_b and b_b:
+        if not isinstance(Cout, BandedMatrix):
+            raise TypeError("banded*banded needs a BandedMatrix destination")
+        # matmul.jl:182-184: non column-major operands are first converted to plain BandedMatrix
+        A2 = materialize_transpose(A) if isinstance(A, Transposed) else A
+        B2 = materialize_transpose(B) if isinstance(B, Transposed) else B
+        return gbmm_(alpha, A2, B2, beta, Cout)
+    if a_b:
+        return _banded_times_dense(alpha, A, B, beta, Cout)
+    if b_b:
+        return _dense_times_banded(alpha, A, B, beta, Cout)
+    raise TypeError("at least one operand must be banded")
+
+
+def materialize_transpose(At: Transposed) -> BandedMatrix:
+    """convert(DefaultBandedMatrix, A') (matmul.jl:182-184): band row r of A' is band row (l+u-r) of A, shifted."""
+    P = At.parent
+    m, n, l, u = P.m, P.n, P.l, P.u
+    rows = max(0, l + u + 1)
+    out = BandedMatrix.zeros((n, m), (u, l), device=P.data.device)
+    # A'[k', j'] = A[j', k'];  out.data[j', l + k' - j'] = P.data[k', u + j' - k']
+    for r in range(rows):  # r = band row of out: k' - j' = r - l
+        d = r - l
+        src_r = u - d  # band row in P: u + j' - k' = u - d
+        j0, j1 = max(0, -d), min(m, n - d)  # j' range with k' = j'+d in [0, n)
+        if j1 > j0:
+            out.data[j0:j1, r] = P.data[j0 + d : j1 + d, src_r]
+    return out
+
+
+def matmul(A, B):
+    """``A*B``: allocates the destination like similar(::MulAdd) (src/generic/matmul.jl:1-6)."""
+    sa, sb = _shape(A), _shape(B)
+    a_b = isinstance(A, (BandedMatrix, Transposed))
+    b_b = isinstance(B, (BandedMatrix, Transposed))
+    dev = (A.parent if isinstance(A, Transposed) else A).data.device if a_b else (
+        B.parent if isinstance(B, Transposed) else B).data.device
+    if len(sb) == 1:
+        if sa[1] != sb[0]:
+            raise DimensionMismatch(f"second dimension of A, {sa[1]}, does not match length of x, {sb[0]}")
+        y = torch.empty(sa[0], dtype=torch.float64, device=dev)
+        return mul_(y, A, B, 1.0, 0.0)
+    if sa[1] != sb[0]:
+        raise DimensionMismatch(f"A has dimensions {sa} but B has dimensions {sb}")
+    if a_b and b_b:
+        (Al, Au), (Bl, Bu) = bandwidths(A), bandwidths(B)
+        bw = (min(sa[0] - 1, Al + Bl), min(sb[1] - 1, Au + Bu))  # bandwidths(M) = min.(_bnds(M), prodbandwidths)
+        Cm = BandedMatrix.undef((sa[0], sb[1]), bw, device=dev)
+        return mul_(Cm, A, B, 1.0, 0.0)
+    Cd = colmajor(sa[0], sb[1], device=dev)
+    return mul_(Cd, A, B, 1.0, 0.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# lu / ldiv! / \
+# ---------------------------------------------------------------------------------------------
+class BandedLU:
+    """``BandedLU{T,S}`` (src/banded/BandedLU.jl:10-19): factors (bandwidths (l, l+u)), HOST ipiv, info."""
+
+    def __init__(self, factors: BandedMatrix, ipiv: np.ndarray, info: int, d_ipiv: torch.Tensor | None = None):
+        self.factors, self.ipiv, self.info = factors, ipiv, int(info)
+        self._d_ipiv = d_ipiv
+
+    @property
+    def shape(self):
+        return self.factors.shape
+
+    @property
+    def T(self):
+        return TransposeFact(self)
+
+    def issuccess(self) -> bool:
+        return self.info == 0
+
+    @property
+    def p(self) -> np.ndarray:
+        """ipiv2perm (BandedLU.jl:125), 1-based like the reference."""
+        m = self.factors.m
+        p = np.arange(1, m + 1)
+        for i, piv in enumerate(self.ipiv):
+            p[i], p[piv - 1] = p[piv - 1], p[i]
+        return p
+
+    def d_ipiv(self) -> torch.Tensor:
+        if self._d_ipiv is None:
+            self._d_ipiv = torch.as_tensor(self.ipiv).to(self.factors.data.device)
+        return self._d_ipiv
+
+
+class TransposeFact:
+    def __init__(self, parent: BandedLU):
+        self.parent = parent
+
+
+def lu_(A: BandedMatrix, check: bool = True) -> BandedLU:
+    """``lu!(A)`` (BandedLU.jl:90-103): A has bandwidths (l, l+u_orig) with zeros in the extra l bands."""
+    m = A.m
+    l, u = A.l, A.u
+    if m == 0:
+        return BandedLU(A, np.zeros(0, dtype=np.int64), 0)
+    hd = _h(A.data)
+    mn = min(m, A.n)
+    d_ipiv = torch.empty(mn, dtype=torch.int64, device=A.data.device)
+    info = C.c_int(0)
+    rc = hd.lib.bmb200_dgbtrf(hd.h, m, A.n, l, u - l, vp(A.ptr), A.lda, vp(d_ipiv.data_ptr()), C.byref(info))
+    if rc < 0 and rc > -100:
+        raise ValueError(f"invalid argument #{-rc} to LAPACK call")  # chklapackerror(info<0) -> ArgumentError
+    hd.check(rc, "dgbtrf")
+    if info.value > 0:
+        raise LAPACKException(info.value)  # gbtrf! -> chklapackerror, BandedLU.jl:98
+    return BandedLU(A, d_ipiv.cpu().numpy(), 0, d_ipiv)
+
+
+def lu(A: BandedMatrix, check: bool = True) -> BandedLU:
+    """``lu(A)`` -> ``_lu`` (BandedLU.jl:108-111): widening copy into (l, l+u) storage, then lu!."""
+    l, u = A.l, A.u
+    if A.m == 0 or A.n == 0:  # zero-size (test_bandedlu.jl:157-164): factors are zeros, no LAPACK call for m == 0
+        W = BandedMatrix.zeros(A.shape, (l, l + u), device=A.data.device)
+        return lu_(W, check)
+    if l < 0 or l + u + 1 <= 0:
+        raise ValueError("invalid argument #1 to LAPACK call")  # gbtrf!(kl<0, ...) -> ArgumentError in the reference
+    W = BandedMatrix.undef(A.shape, (l, l + u), device=A.data.device)
+    hd = _h(A.data)
+    hd.check(hd.lib.bmb200_dband_widen(hd.h, A.n, l, u, vp(A.ptr), A.lda, vp(W.ptr), W.lda), "dband_widen")
+    return lu_(W, check)
+
+
+def ldiv_(F, B: torch.Tensor) -> torch.Tensor:
+    """``ldiv!(F, B)`` (linalg.jl:24-30) and ``ldiv!(transpose(F), B)`` (:41-47); B is overwritten."""
+    trans = "N"
+    if isinstance(F, TransposeFact):
+        F, trans = F.parent, "T"
+    A = F.factors
+    m = A.m
+    if B.shape[0] != m:
+        raise DimensionMismatch(f"B has first dimension {B.shape[0]} but needs {m}")
+    if m == 0:
+        return B
+    l, u = A.l, A.u
+    hd = _h(B)
+    nrhs = 1 if B.dim() == 1 else B.shape[1]
+    if B.dim() == 1 and _inc(B) != 1:
+        raise TypeError("right-hand side vector must be contiguous")
+    ldb = max(1, m) if B.dim() == 1 else _ld(B)
+    rc = hd.lib.bmb200_dgbtrs(hd.h, trans.encode(), m, l, u - l, nrhs, vp(A.ptr), A.lda, vp(F.d_ipiv().data_ptr()),
+                              vp(B.data_ptr()), ldb)
+    hd.check(rc, "dgbtrs")
+    return B
+
+
+def factorize(A: BandedMatrix):
+    """_factorize (linalg.jl:75): square -> lu; rectangular -> qr (out of scope here)."""
+    if A.m != A.n:
+        raise NotImplementedError("rectangular banded solves use banded QR in the reference (out of scope)")
+    return lu(A)
+
+
+def solve(A, b: torch.Tensor) -> torch.Tensor:
+    """``A \\ b`` (linalg.jl:5-9): copies b, checks squareness, factorises, ldiv!."""
+    if isinstance(A, (BandedLU, TransposeFact)):
+        return ldiv_(A, b.clone() if b.dim() == 1 else _clone_cm(b))
+    if A.m != A.n:  # checksquare
+        raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")
+    if b.shape[0] != A.m:
+        raise DimensionMismatch(f"B has first dimension {b.shape[0]} but needs {A.m}")
+    return ldiv_(factorize(A), b.clone() if b.dim() == 1 else _clone_cm(b))
+
+
+def _clone_cm(X: torch.Tensor) -> torch.Tensor:
+    out = colmajor(X.shape[0], X.shape[1], device=X.device)
+    out.copy_(X)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# host-buffer entry points (the Fortran-ABI drop-in with HOST arrays; bench.py's e2e)
+# ---------------------------------------------------------------------------------------------
+def gbmv_host(trans, m, kl, ku, alpha, data: np.ndarray, x: np.ndarray, beta, y: np.ndarray, device=0):
+    """BLAS.gbmv!(trans, m, kl, ku, α, data, x, β, y) on HOST arrays; data is (lda x n) Fortran-ordered."""
+    hd = _lib.handle(device)
+    n = data.shape[1]
+    lda = data.strides[1] // 8 if n > 1 else max(1, data.shape[0])
+    incx = x.strides[0] // 8 if x.size > 1 else 1
+    incy = y.strides[0] // 8 if y.size > 1 else 1
+    hd.check(hd.lib.bmb200_dgbmv_host(hd.h, trans.encode(), m, n, kl, ku, float(alpha), vp(data.ctypes.data), lda,
+                                      vp(x.ctypes.data), incx, float(beta), vp(y.ctypes.data), incy), "dgbmv_host")
+    return y

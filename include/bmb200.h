@@ -1,0 +1,143 @@
+/*
+ * bmb200.h -- C ABI of libbmb200.so: the B200 (sm_100a) banded hot path behind
+ * BandedMatrices.jl's mul! / * / lu / ldiv! / \ .
+ *
+ * Every entry point replaces one native call (or one pure-Julia driver loop) of the
+ * reference; the citation beside each says which (paths relative to the reference root).
+ * The library is what a `ccall((:bmb200_xxx, libbmb200), ...)` in the Julia glue binds
+ * (julia/BandedMatricesB200.jl) and what the Python ctypes host mirror
+ * (bandedmatrices.jl_b200/) binds in this repository.
+ *
+ * Conventions
+ *   - plain C, by-value scalars, raw pointers; no torch / C++ types cross the boundary.
+ *   - all matrices are Float64, column-major, in LAPACK general-band storage:
+ *       band storage  A[k,j] at a[(ku + k - j) + j*lda]     (0-based; src/banded/BandedMatrix.jl:414-419)
+ *       LU storage    ldab >= 2*kl+ku+1, A[k,j] at ab[(kl + ku + k - j) + j*ldab]
+ *   - pointers named d* are DEVICE pointers (HBM resident); h* are HOST pointers.
+ *   - ipiv is 1-based int64 exactly as LAPACK/Julia (`Vector{BlasInt}`, src/banded/BandedLU.jl:12).
+ *   - return value: 0 ok; -i = the i-th argument (1-based, counting the handle) is invalid
+ *     (LAPACK xerbla convention); BMB200_ERR_CUDA (-1000 - cudaError) for runtime failures.
+ *     For gbtrf the LAPACK `info` (> 0: first exactly-zero pivot, factorisation completed) is
+ *     returned through *info.
+ *   - calls are asynchronous on the handle's stream unless they return host-visible data.
+ *   - there is NO CPU fallback: a call that cannot run on the device fails loudly.
+ */
+#ifndef BMB200_H
+#define BMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMB200_ERR_CUDA (-1000)
+#define BMB200_VERSION 100
+
+typedef struct bmb200_ctx *bmb200_handle_t;
+
+/* ---- context / memory (plumbing the Julia glue needs for its device array type) ---- */
+int bmb200_version(void);
+/* stream may be NULL (legacy default stream) or a cudaStream_t owned by the caller. */
+int bmb200_create(bmb200_handle_t *h, int device, void *stream);
+int bmb200_destroy(bmb200_handle_t h);
+int bmb200_set_stream(bmb200_handle_t h, void *stream);
+int bmb200_sync(bmb200_handle_t h);
+int bmb200_malloc(bmb200_handle_t h, void **dptr, size_t bytes);
+int bmb200_free(bmb200_handle_t h, void *dptr);
+int bmb200_memcpy_h2d(bmb200_handle_t h, void *dst, const void *hsrc, size_t bytes);
+int bmb200_memcpy_d2h(bmb200_handle_t h, void *hdst, const void *dsrc, size_t bytes);
+const char *bmb200_last_error(bmb200_handle_t h);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t bmb200_launch_count(bmb200_handle_t h);
+
+/* ---- y <- alpha*op(A)*x + beta*y ------------------------------------------------------
+ * Replaces dgbmv_ : src/blas.jl:16-28 (pointer form) and BLAS.gbmv! reached from
+ * src/generic/matmul.jl:21-23.  Same argument list as the Fortran routine.  trans in
+ * {'N','T','C'}.  beta == 0 overwrites y (NaN/Inf in y do not propagate); alpha == 0 only
+ * scales; out-of-matrix corner slots of dA are never read.  'N' accumulates every y[i] in
+ * ascending-column order with one FMA per term, t = alpha*x[j] rounded first -- the order
+ * OpenBLAS' dgbmv_n uses -- so results are bit-identical to the reference CPU path.      */
+int bmb200_dgbmv(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
+                 double alpha, const double *dA, int64_t lda, const double *dx, int64_t incx,
+                 double beta, double *dy, int64_t incy);
+
+/* ---- C <- alpha*A*B + beta*C, all three banded -----------------------------------------
+ * Replaces _gbmm! : src/banded/gbmm.jl:296-340 (the per-column dgbmv_ loop in three regimes
+ * plus the trailing beta-fill), one launch instead of m BLAS calls.  A is n x nu with
+ * (Al,Au), B is nu x m with (Bl,Bu), C is n x m and dC points at the first WRITTEN band row
+ * (gbmm.jl:289) with (Cl,Cu) = min((n-1,m-1),(Al+Bl,Au+Bu)); lda/ldb/ldc are the column
+ * strides.  All band widths >= 0 (the gbmm! driver has already pruned negative ones).     */
+int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t m, int64_t Al, int64_t Au,
+                    int64_t Bl, int64_t Bu, int64_t Cl, int64_t Cu, double alpha, const double *dA,
+                    int64_t lda, const double *dB, int64_t ldb, double beta, double *dC, int64_t ldc);
+
+/* ---- C <- alpha*op(A)*B + beta*C, A banded m x n, B/C dense column-major, nrhs columns ----
+ * Replaces the per-column mul! loop of src/generic/matmul.jl:243-256 (one dgbmv_ per column
+ * of B): A is streamed once for all right-hand sides.                                      */
+int bmb200_dgbmm_bd(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
+                    int64_t nrhs, double alpha, const double *dA, int64_t lda, const double *dB,
+                    int64_t ldb, double beta, double *dC, int64_t ldc);
+
+/* ---- C <- beta*C on a rows x cols column-major block; beta == 0 zero-fills ----------------
+ * Replaces _fill_lmul!/_fill_rmul! : src/generic/utils.jl:29-31 (used by gbmm.jl:287-288,339
+ * and matmul.jl:31-33,45,52).  inc is the element stride inside a column (1 for matrices).  */
+int bmb200_dfill_lmul(bmb200_handle_t h, double beta, double *dC, int64_t rows, int64_t cols,
+                      int64_t ldc, int64_t inc);
+
+/* ---- widening copy of lu(A): (l+u+1) x n band data -> (2l+u+1) x n, top l rows zero ---------
+ * Replaces BandedMatrix{T}(A,(l,l+u)) at src/banded/BandedLU.jl:110 (scalar loop at
+ * src/banded/BandedMatrix.jl:222-232).                                                     */
+int bmb200_dband_widen(bmb200_handle_t h, int64_t n, int64_t l, int64_t u, const double *dA,
+                       int64_t lda, double *dAB, int64_t ldab);
+
+/* ---- partial-pivot band LU -------------------------------------------------------------
+ * Replaces dgbtrf_ reached through LAPACK.gbtrf!(kl, ku, m, AB) at src/banded/BandedLU.jl:98.
+ * dAB is (ldab >= 2kl+ku+1) x n in LU storage and is overwritten by the factors in LAPACK's
+ * format (multipliers not row-permuted, BandedLU.jl:7-8).  d_ipiv: min(m,n) int64 on the
+ * DEVICE (1-based); the host copy the reference keeps in BandedLU.ipiv is fetched by the
+ * caller with bmb200_memcpy_d2h.  Pivot choice = first maximum of |.|, multipliers scaled by
+ * the reciprocal, updates are one FMA per term in ascending column order: pivots AND factors
+ * are bit-identical to DGBTF2.  *info (host) receives the LAPACK info; the call synchronises. */
+int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, double *dAB,
+                  int64_t ldab, int64_t *d_ipiv, int *info);
+
+/* ---- solve with the factors ------------------------------------------------------------
+ * Replaces dgbtrs_ reached through LAPACK.gbtrs!(trans, kl, ku, m, AB, ipiv, B) at
+ * src/banded/linalg.jl:28 ('N'), :46 ('T'), :62 ('C').  dB is n x nrhs, overwritten by X.    */
+int bmb200_dgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t kl, int64_t ku, int64_t nrhs,
+                  const double *dAB, int64_t ldab, const int64_t *d_ipiv, double *dB, int64_t ldb);
+
+/* ---- host-buffer forms: what a Fortran-ABI caller with HOST arrays gets (bench.py "e2e") ----
+ * Same semantics as the calls above; inputs are copied host->device in pipelined chunks, the
+ * result is copied back, and the call returns after the result is in host memory.           */
+int bmb200_dgbmv_host(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
+                      double alpha, const double *hA, int64_t lda, const double *hx, int64_t incx,
+                      double beta, double *hy, int64_t incy);
+int bmb200_dgbsv_host(bmb200_handle_t h, int64_t n, int64_t kl, int64_t ku, int64_t nrhs,
+                      double *hAB, int64_t ldab, int64_t *h_ipiv, double *hB, int64_t ldb, int *info);
+int bmb200_dgbmm_bb_host(bmb200_handle_t h, int64_t n, int64_t nu, int64_t m, int64_t Al, int64_t Au,
+                         int64_t Bl, int64_t Bu, int64_t Cl, int64_t Cu, double alpha, const double *hA,
+                         int64_t lda, const double *hB, int64_t ldb, double beta, double *hC, int64_t ldc);
+
+/* ---- multi-GPU: row-sharded gbmv with an (l+u) halo of x over NVLink peer memory ------------
+ * One process per GPU.  Rank r owns rows/columns [c0, c1) of a square
+ * n x n matrix: dA_local holds data columns [c0, c1), dx_local / dy_local the matching slices.
+ * bmb200_halo_* wires the per-rank halo mailboxes (CUDA IPC handles exchanged by the host
+ * plumbing, e.g. torch.distributed); bmb200_dgbmv_sharded pushes the kl/ku boundary entries of
+ * x into the neighbours' mailboxes with peer stores, signals, waits for its own halo and runs
+ * the same streaming kernel on the local slab.  No reduction, no NCCL on the data path.       */
+#define BMB200_IPC_HANDLE_BYTES 64
+int bmb200_halo_create(bmb200_handle_t h, int64_t max_halo, void *ipc_handle_out /* 64 bytes */);
+int bmb200_halo_connect(bmb200_handle_t h, int rank, int nranks, const void *ipc_left /* or NULL */,
+                        const void *ipc_right /* or NULL */);
+int bmb200_halo_destroy(bmb200_handle_t h);
+int bmb200_dgbmv_sharded(bmb200_handle_t h, int64_t n_global, int64_t c0, int64_t c1, int64_t kl,
+                         int64_t ku, double alpha, const double *dA_local, int64_t lda,
+                         const double *dx_local, double beta, double *dy_local);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMB200_H */

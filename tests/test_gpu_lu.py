@@ -1,0 +1,127 @@
+"""GPU parity: lu / lu! / ldiv! / \\ through the C ABI vs the oracle.  Pivots AND factors bit-identical to
+DGBTF2, solutions bit-identical to DGBTRS 'N'; transposed solves to tolerance; residual bound from
+north_star (relative residual <= 1e-12 * cond).  Shapes from test/test_bandedlu.jl."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import Band, brand, ldiv, lu
+
+from _util import golden_cases, kat_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def up(bm, Bd: Band):
+    return bm.BandedMatrix.from_banddata(Bd.data, Bd.m, Bd.l, Bd.u)
+
+
+def test_golden_lu(bm):
+    for cid, c in golden_cases("lu"):
+        n, l, u, nrhs, info = (int(v) for v in c["dims"])
+        F = bm.lu(bm.BandedMatrix.from_banddata(c["data"], n, l, u))
+        assert np.array_equal(F.ipiv, c["ipiv"]), cid                       # pivots bit-identical
+        got = F.factors.banddata_host()
+        if u > 64 and l >= 32:   # fixture produced by OpenBLAS' blocked DGBTRF: DGEMM rounding differs
+            assert np.max(np.abs(got - c["ab"])) < 1e-10, cid
+        else:
+            assert np.array_equal(got, c["ab"]), cid                        # factors bit-identical
+        Fg = bm.BandedLU(bm.BandedMatrix.from_banddata(c["ab"], n, l, l + u), c["ipiv"], 0)
+        X = bm.to_colmajor(c["B"])
+        bm.ldiv_(Fg, X)
+        assert np.array_equal(X.cpu().numpy(), c["X"]), cid                 # solve bit-identical
+        XT = bm.to_colmajor(c["B"])
+        bm.ldiv_(Fg.T, XT)
+        assert np.max(np.abs(XT.cpu().numpy() - c["XT"])) <= 1e-10 * np.max(np.abs(c["XT"])), cid
+
+
+@pytest.mark.parametrize("shape", [(1000, 4, 3, 1), (10000, 4, 3, 1), (5000, 16, 16, 8), (3000, 5, 7, 5), (64, 3, 2, 2),
+                                   (2000, 64, 64, 2), (1, 0, 0, 1), (5, 4, 4, 1), (2000, 0, 3, 2), (2000, 3, 0, 2),
+                                   (4000, 1, 1, 4), (3000, 31, 0, 3), (3000, 33, 31, 2), (6, 7, 9, 1)])
+def test_lu_solve_bit_identical(bm, oracle_c, rng, shape):
+    n, l, u, nrhs = shape
+    A = brand(rng, n, n, l, u)
+    ab, ipiv, info = lu(oracle_c, A)
+    F = bm.lu(up(bm, A))
+    assert F.info == 0 and F.issuccess()
+    assert (F.factors.l, F.factors.u) == (l, l + u)
+    assert np.array_equal(F.ipiv, ipiv)
+    assert np.array_equal(F.factors.banddata_host(), ab)
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    ref = B.copy(order="F")
+    ldiv(oracle_c, "N", ab, ipiv, l, u, ref)
+    X = bm.to_colmajor(B)
+    bm.ldiv_(F, X)
+    assert np.array_equal(X.cpu().numpy(), ref)
+    refT = B.copy(order="F")
+    ldiv(oracle_c, "T", ab, ipiv, l, u, refT)
+    XT = bm.to_colmajor(B)
+    bm.ldiv_(F.T, XT)
+    assert np.max(np.abs(XT.cpu().numpy() - refT)) <= 1e-9 * max(1e-300, np.max(np.abs(refT)))
+    # vector right-hand side and A \ b (b not overwritten: test_bandedlu.jl:22-23)
+    b = torch.as_tensor(B[:, 0].copy()).cuda()
+    b_keep = b.clone()
+    x = bm.solve(up(bm, A), b)
+    assert torch.equal(b, b_keep)
+    assert np.array_equal(x.cpu().numpy(), ref[:, 0])
+
+
+def test_residual_bound(bm, rng):
+    """north_star: relative residual <= 1e-12 * cond (here cond is computed densely at n = 400)."""
+    n, l, u = 400, 16, 16
+    A = brand(rng, n, n, l, u)
+    D = A.dense()
+    b = rng.standard_normal(n)
+    x = bm.solve(up(bm, A), torch.as_tensor(b).cuda()).cpu().numpy()
+    res = np.linalg.norm(D @ x - b) / (np.linalg.norm(D, 2) * np.linalg.norm(x))
+    assert res <= 1e-12 * np.linalg.cond(D)
+    assert res <= 1e-13
+
+
+def test_lu_kat_pivot_vector(bm):
+    """L,U,p = lu(A): the pivot vector equals dense LU's (test_bandedlu.jl:26-38) on the integer KAT matrix."""
+    import scipy.linalg as sl
+
+    D, v, X = kat_matrix()
+    F = bm.lu(bm.BandedMatrix.from_dense(D, (2, 2)))
+    _, piv = sl.lu_factor(D)
+    assert np.array_equal(F.ipiv, piv + 1)
+    sol = bm.solve(bm.BandedMatrix.from_dense(D, (2, 2)), bm.to_colmajor(X)).cpu().numpy()
+    assert np.allclose(D @ sol, X, rtol=1e-10, atol=1e-9)
+
+
+def test_singular_raises(bm):
+    D = np.diag([1.0, 2.0, 0.0, 4.0, 5.0, 6.0])
+    with pytest.raises(bm.LAPACKException) as e:
+        bm.lu(bm.BandedMatrix.from_dense(D, (1, 1)))
+    assert e.value.info == 3
+
+
+def test_zero_size_and_nonsquare(bm):
+    """test_bandedlu.jl:157-164 (0x0, 0x3, negative bandwidths) and :79-87 (non-square ⇒ DimensionMismatch)."""
+    for (m, n, l, u) in [(0, 0, 1, 1), (0, 3, 1, 1), (0, 0, -1, -1)]:
+        A = bm.BandedMatrix.zeros((m, n), (l, u))
+        F = bm.lu(A)
+        assert F.ipiv.size == 0 and not F.factors.data.any()
+    A0 = bm.BandedMatrix.zeros((0, 0), (1, 1))
+    assert bm.solve(A0, torch.zeros(0, dtype=torch.float64, device="cuda")).numel() == 0
+    R = bm.brand(6, 7, 1, 1, seed=1)
+    with pytest.raises(bm.DimensionMismatch):
+        bm.solve(R, torch.zeros(6, dtype=torch.float64, device="cuda"))
+
+
+def test_lu_large_c4_shape_scaled(bm, oracle_ob, rng):
+    """C4's band (16,16) at n = 2^16 with 8 RHS: pivots / factors / solution bit-identical to OpenBLAS itself."""
+    n, l, u, nrhs = 1 << 16, 16, 16, 8
+    A = brand(rng, n, n, l, u)
+    ab, ipiv, info = lu(oracle_ob, A)
+    F = bm.lu(up(bm, A))
+    assert np.array_equal(F.ipiv, ipiv)
+    assert np.array_equal(F.factors.banddata_host(), ab)
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    ref = B.copy(order="F")
+    ldiv(oracle_ob, "N", ab, ipiv, l, u, ref)
+    X = bm.to_colmajor(B)
+    bm.ldiv_(F, X)
+    assert np.array_equal(X.cpu().numpy(), ref)

@@ -1,0 +1,78 @@
+"""CPU: the host-side data model (storage rule, views, transposes, band counting) on CPU tensors.
+Kernels are never called here."""
+import numpy as np
+import pytest
+import torch
+
+import bandedmatrices_b200 as bm
+from bandedmatrices_b200.linalg import _num_zeroband_l, _num_zeroband_u, materialize_transpose
+
+
+def _rand_banded(rng, m, n, l, u):
+    D = rng.standard_normal((m, n))
+    return np.triu(np.tril(D, u), -l) if -l <= u else np.zeros((m, n))
+
+
+@pytest.mark.parametrize("shape", [(10, 12, 2, 3), (12, 10, 3, 2), (7, 7, 0, 0), (5, 9, 1, 6), (9, 5, 6, 1), (10, 10, -1, 2),
+                                   (10, 10, 2, -1), (1, 10, 0, 9), (6, 6, 8, 8)])
+def test_storage_rule_roundtrip(rng, shape):
+    m, n, l, u = shape
+    D = _rand_banded(rng, m, n, l, u)
+    A = bm.BandedMatrix.from_dense(D, (l, u), device="cpu")
+    assert A.data.shape == (n, max(0, l + u + 1))
+    # data[u+k-j, j] = A[k,j]  (src/banded/BandedMatrix.jl:414-419)
+    d = A.banddata_host()
+    for j in range(n):
+        for k in range(max(0, j - u), min(m - 1, j + l) + 1):
+            assert d[u + k - j, j] == D[k, j]
+    assert np.array_equal(A.to_dense(), D)
+    assert bm.bandwidths(A) == (l, u) and bm.bandwidths(A.T) == (u, l)
+    assert bm.bandeddata(A).shape == (max(0, l + u + 1), n)
+
+
+def test_views_shift_bandwidths(rng):
+    m, n, l, u = 11, 13, 3, 2
+    D = _rand_banded(rng, m, n, l, u)
+    A = bm.BandedMatrix.from_dense(D, (l, u), device="cpu")
+    for s in (0, 1, 2, 4):
+        V = A.view_cols(s)
+        assert (V.l, V.u) == (l + s, u - s) and V.shape == (m, n - s)
+        assert np.array_equal(V.to_dense(), D[:, s:])
+        W = A.view_rows(s)
+        assert (W.l, W.u) == (l - s, u + s) and W.shape == (m - s, n)
+        assert np.array_equal(W.to_dense(), D[s:, :])
+
+
+def test_materialize_transpose(rng):
+    for (m, n, l, u) in [(8, 11, 2, 3), (11, 8, 0, 4), (6, 6, 1, 0)]:
+        D = _rand_banded(rng, m, n, l, u)
+        A = bm.BandedMatrix.from_dense(D, (l, u), device="cpu")
+        T = materialize_transpose(A.T)
+        assert (T.l, T.u) == (u, l)
+        assert np.array_equal(T.to_dense(), D.T)
+
+
+def test_num_zerobands(rng):
+    D = _rand_banded(rng, 9, 9, 2, 3)
+    D[np.arange(6), np.arange(6) + 3] = 0  # top band all zero
+    D[np.arange(7), np.arange(7) + 2] = 0
+    A = bm.BandedMatrix.from_dense(D, (2, 3), device="cpu")
+    assert _num_zeroband_u(A) == 2 and _num_zeroband_l(A) == 0
+    Z = bm.BandedMatrix.from_dense(np.zeros((5, 5)), (1, 1), device="cpu")
+    assert _num_zeroband_u(Z) == 3 and _num_zeroband_l(Z) == 3
+
+
+def test_constructor_checks():
+    with pytest.raises(ValueError):  # BandedMatrix.jl:22-24
+        bm.BandedMatrix(torch.zeros((5, 4), dtype=torch.float64), 5, 1, 1)
+    with pytest.raises(TypeError):
+        bm.BandedMatrix(torch.zeros((5, 3), dtype=torch.float32), 5, 1, 1)
+
+
+def test_dimension_checks_before_any_kernel():
+    A = bm.BandedMatrix(torch.zeros((6, 3), dtype=torch.float64), 6, 1, 1)
+    with pytest.raises(bm.DimensionMismatch):  # test/test_linalg.jl:333-338
+        bm.mul_(torch.zeros(6, dtype=torch.float64), A, torch.zeros(5, dtype=torch.float64))
+    R = bm.BandedMatrix(torch.zeros((7, 3), dtype=torch.float64), 6, 1, 1)
+    with pytest.raises(bm.DimensionMismatch):  # non-square solve, test/test_bandedlu.jl:79-87
+        bm.solve(R, torch.zeros(6, dtype=torch.float64))

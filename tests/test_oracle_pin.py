@@ -1,0 +1,175 @@
+"""CPU: pins the oracle.  (1) the C restatement (oracle/bmoracle.c) against the OpenBLAS 0.3.30 ILP64 library
+numpy ships -- the Fortran entry points the reference ccalls -- bit-for-bit where the operation order is defined
+(gbmv 'N', gbtf2, gbtrs 'N') and to tolerance elsewhere; (2) both against the committed golden fixtures; (3) both
+against the reference's deterministic integer KAT (test/test_linalg.jl:51-97) and dense arithmetic."""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import Band, band_from_dense, banded_muladd_vec, brand, gbmm_kernel, gbmv, ldiv, lu
+
+from _util import golden_cases, kat_matrix, scalar
+
+
+def test_openblas_identity(oracle_ob):
+    assert "OpenBLAS 0.3.30" in oracle_ob.config and "USE64BITINT" in oracle_ob.config
+
+
+@pytest.mark.parametrize("shape", [(100, 100, 4, 3), (40, 55, 2, 5), (55, 40, 5, 2), (300, 300, 32, 32), (10, 10, 0, 0),
+                                   (1, 10, 0, 9), (50, 50, 1, 0), (10, 10, 12, 15)])
+def test_c_gbmv_matches_openblas(oracle_c, oracle_ob, rng, shape):
+    m, n, kl, ku = shape
+    for (al, be) in [(1.0, 0.0), (2.0, 3.0), (0.123, 0.456), (0.0, 0.0), (0.0, 2.0), (1.0, 1.0)]:
+        A = brand(rng, m, n, kl, ku, corners=np.nan)  # NaN corners: must never be read
+        for tr in "NT":
+            x = rng.standard_normal(n if tr == "N" else m)
+            y0 = rng.standard_normal(m if tr == "N" else n)
+            if be == 0.0:
+                y0[:] = np.nan  # beta == 0 overwrites (test/test_linalg.jl:225-270)
+            y1, y2 = y0.copy(), y0.copy()
+            gbmv(oracle_c, tr, m, kl, ku, al, A.data, x, be, y1)
+            gbmv(oracle_ob, tr, m, kl, ku, al, A.data, x, be, y2)
+            if tr == "N":
+                assert np.array_equal(y1, y2)
+            else:
+                assert np.allclose(y1, y2, rtol=1e-13, atol=1e-13)
+            D = A.dense()
+            ref = al * ((D @ x) if tr == "N" else (D.T @ x)) + (0 if be == 0 else be * y0)
+            assert np.allclose(y1, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_c_gbmv_strided(oracle_c, oracle_ob, rng):
+    m, n, kl, ku = 30, 40, 3, 2
+    A = brand(rng, m, n, kl, ku)
+    xs, ys = rng.standard_normal(3 * n), rng.standard_normal(2 * m)
+    y1, y2 = ys.copy(), ys.copy()
+    gbmv(oracle_c, "N", m, kl, ku, 1.5, A.data, xs[::3], 0.5, y1[::2])
+    gbmv(oracle_ob, "N", m, kl, ku, 1.5, A.data, xs[::3], 0.5, y2[::2])
+    assert np.array_equal(y1, y2)
+
+
+def test_c_gbmm_regimes_match_openblas_all_shapes(oracle_c, oracle_ob, rng):
+    """The reference's own gbmm! sweep (test/test_linalg.jl:212-222): 3^3 * 4^4 = 6912 shape combinations."""
+    L = oracle_c.L
+    cnt = 0
+    for n, nu, m in itertools.product([1, 5, 50], repeat=3):
+        for Al, Au, Bl, Bu in itertools.product([0, 1, 2, 30], repeat=4):
+            A = brand(rng, n, nu, Al, Au, corners=np.nan)
+            B = brand(rng, nu, m, Bl, Bu, corners=np.nan)
+            Cl, Cu = min(n - 1, Al + Bl), min(m - 1, Au + Bu)
+            C0 = brand(rng, n, m, Cl, Cu)
+            c1, c2, c3 = (C0.data.copy(order="F") for _ in range(3))
+            gbmm_kernel(oracle_c, 0.123, A.data, B.data, 0.456, c1, n, nu, m, Al, Au, Bl, Bu, Cl, Cu)
+            gbmm_kernel(oracle_ob, 0.123, A.data, B.data, 0.456, c2, n, nu, m, Al, Au, Bl, Bu, Cl, Cu)
+            L.oracle_gbmm(n, nu, m, Al, Au, Bl, Bu, Cl, Cu, 0.123, A.data.ctypes.data, A.data.shape[0],
+                          B.data.ctypes.data, B.data.shape[0], 0.456, c3.ctypes.data, c3.shape[0])
+            assert np.array_equal(c1, c2) and np.array_equal(c1, c3)
+            if cnt % 16 == 0:
+                D = 0.123 * A.dense() @ B.dense() + 0.456 * C0.dense()
+                assert np.allclose(Band(c1, n, Cl, Cu).dense(), D, rtol=1e-12, atol=1e-12)
+            cnt += 1
+    assert cnt == 6912
+
+
+@pytest.mark.parametrize("shape", [(1000, 4, 3, 1), (500, 16, 16, 3), (300, 5, 7, 5), (64, 3, 2, 2), (400, 64, 64, 2),
+                                   (1, 0, 0, 1), (5, 4, 4, 1), (200, 0, 3, 2), (200, 3, 0, 2), (128, 1, 1, 4)])
+def test_c_lu_solve_bit_identical_to_openblas(oracle_c, oracle_ob, rng, shape):
+    n, kl, ku, nrhs = shape
+    A = brand(rng, n, n, kl, ku)
+    ab1, p1, i1 = lu(oracle_c, A)
+    ab2, p2, i2 = lu(oracle_ob, A)
+    assert i1 == i2 == 0
+    assert np.array_equal(p1, p2)          # pivots bit-identical
+    assert np.array_equal(ab1, ab2)        # unblocked regime: factors bit-identical
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    for tr in "NT":
+        b1, b2 = B.copy(order="F"), B.copy(order="F")
+        ldiv(oracle_c, tr, ab2, p2, kl, ku, b1)
+        ldiv(oracle_ob, tr, ab2, p2, kl, ku, b2)
+        if tr == "N":
+            assert np.array_equal(b1, b2)
+        else:
+            assert np.max(np.abs(b1 - b2)) <= 1e-11 * np.max(np.abs(b2))
+
+
+@pytest.mark.parametrize("shape", [(300, 70, 70), (260, 100, 65), (400, 128, 128)])
+def test_c_lu_blocked_regime_pivots_equal(oracle_c, oracle_ob, rng, shape):
+    """ku > 64 and kl >= 32: OpenBLAS runs LAPACK's blocked DGBTRF (DTRSM+DGEMM rounding): pivots equal, factors ~."""
+    n, kl, ku = shape
+    A = brand(rng, n, n, kl, ku)
+    ab1, p1, _ = lu(oracle_c, A)
+    ab2, p2, _ = lu(oracle_ob, A)
+    assert np.array_equal(p1, p2)
+    assert np.max(np.abs(ab1 - ab2)) < 1e-10
+
+
+def test_c_lu_singular_info(oracle_c, oracle_ob):
+    A = Band(np.asfortranarray(np.zeros((3, 6))), 6, 1, 1)
+    A.data[1, :] = [1, 2, 0, 4, 5, 6]  # zero diagonal at column 3, no off-diagonals -> info = 3
+    _, _, i1 = lu(oracle_c, A)
+    _, _, i2 = lu(oracle_ob, A)
+    assert i1 == i2 == 3
+
+
+def test_kat_integer_valued(oracle_c, oracle_ob):
+    """test/test_linalg.jl:51-97: exact in Float64 because every operand is a small integer."""
+    D, v, X = kat_matrix()
+    A = band_from_dense(D, 2, 2)
+    for be_ in (oracle_c, oracle_ob):
+        for (al, bt) in [(1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (2.0, 3.0)]:
+            y = v.copy()
+            banded_muladd_vec(be_, al, A, v, bt, y)
+            assert np.array_equal(y, al * (D @ v) + bt * v)
+        ab, ipiv, info = lu(be_, A)
+        assert info == 0
+        sol = np.asfortranarray(X.copy())
+        ldiv(be_, "N", ab, ipiv, 2, 2, sol)
+        assert np.allclose(D @ sol, X, rtol=1e-10, atol=1e-10)
+
+
+def test_negative_bandwidth_driver(oracle_c, rng):
+    """_banded_muladd! re-viewing (src/generic/matmul.jl:41-59); shapes of test/test_banded.jl:97-140."""
+    for (m, n, l, u) in [(10, 12, 2, 3), (10, 12, -2, 2), (10, 12, 2, -2), (10, 12, 2, -3), (12, 10, -1, 1), (8, 8, 1, -1),
+                         (8, 8, -2, 1)]:
+        D = np.triu(np.tril(rng.standard_normal((m, n)), u), -l) if -l <= u else np.zeros((m, n))
+        A = band_from_dense(D, l, u)
+        x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+        y = y0.copy()
+        banded_muladd_vec(oracle_c, 2.0, A, x, 3.0, y)
+        assert np.allclose(y, 2.0 * D @ x + 3.0 * y0, rtol=1e-13, atol=1e-13), (m, n, l, u)
+
+
+def test_golden_gbmv(oracle_c):
+    for cid, c in golden_cases("gbmv"):
+        m, l, u = (int(scalar(c[k])) for k in ("m", "l", "u"))
+        tr = str(scalar(c["trans"]))
+        y = c["y0"].copy()
+        gbmv(oracle_c, tr, m, l, u, float(c["alpha"]), np.asfortranarray(c["data"]), c["x"], float(c["beta"]), y)
+        if tr == "N":
+            assert np.array_equal(y, c["y"]), cid
+        else:
+            assert np.allclose(y, c["y"], rtol=1e-13, atol=1e-13), cid
+
+
+def test_golden_gbmm(oracle_c):
+    for cid, c in golden_cases("gbmm"):
+        n, nu, m, Al, Au, Bl, Bu, Cl, Cu = (int(v) for v in c["dims"])
+        out = np.asfortranarray(c["C0"].copy())
+        gbmm_kernel(oracle_c, 0.123, np.asfortranarray(c["A"]), np.asfortranarray(c["B"]), 0.456, out, n, nu, m, Al, Au, Bl,
+                    Bu, Cl, Cu)
+        assert np.array_equal(out, c["C"]), cid
+
+
+def test_golden_lu(oracle_c):
+    for cid, c in golden_cases("lu"):
+        n, l, u, nrhs, info = (int(v) for v in c["dims"])
+        A = Band(np.asfortranarray(c["data"]), n, l, u)
+        ab, ipiv, inf = lu(oracle_c, A)
+        assert inf == info and np.array_equal(ipiv, c["ipiv"]), cid
+        if not (u > 64 and l >= 32):
+            assert np.array_equal(ab, c["ab"]), cid
+        X = np.asfortranarray(c["B"].copy())
+        ldiv(oracle_c, "N", np.asfortranarray(c["ab"]), c["ipiv"], l, u, X)
+        assert np.array_equal(X, c["X"]), cid
