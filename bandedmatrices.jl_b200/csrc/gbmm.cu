@@ -25,6 +25,9 @@ gbmm_bb_sweep(i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 
     for (i64 j = warp; j < m; j += nwarps) {
         i64 k0 = j - Cu; if (k0 < 0) k0 = 0;
         i64 k1 = j + Cl; if (k1 > n - 1) k1 = n - 1;
+        // columns right of every B column that meets A (j >= nu+Bu): the reference beta-fills the WHOLE band
+        // column, out-of-matrix slots included (_fill_lmul!(beta, view(C_data,:,nu+Bu+1:min(m,n+Cu))), gbmm.jl:339)
+        if (j >= nu + Bu && j < n + Cu) { k0 = j - Cu; k1 = j + Cl; }
         i64 v0 = j - Bu; if (v0 < 0) v0 = 0;
         i64 v1 = j + Bl; if (v1 > nu - 1) v1 = nu - 1;
         const double *bcol = b + j * ldb + (Bu - j);   // B[v,j] = bcol[v]
