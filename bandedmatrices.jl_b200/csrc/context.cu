@@ -62,6 +62,14 @@ extern "C" int bmb200_sync(bmb200_handle_t h)
     if (!h) return -1;
     DeviceGuard g(h->device);
     BMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    // a sharded gbmv whose neighbour never published its halo raises a device-side flag instead of hanging
+    int flag = 0;
+    BMB_CUDA(h, cudaMemcpy(&flag, h->d_info + 8, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(h->d_info + 8, 0, sizeof(int));
+        snprintf(h->err, sizeof(h->err), "dgbmv_sharded: timed out waiting for a neighbour's x halo");
+        return BMB200_ERR_CUDA;
+    }
     return 0;
 }
 

@@ -15,114 +15,19 @@
 //   gbmv_t_lane<W,LDV>      'T', narrow: lane = column, dot with the x window.
 //   gbmv_t_warp             'T', any width: warp = column, shuffle reduction.
 #include "common.cuh"
+#include "gbmv_systolic.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// Narrow-band streaming kernel ('N')
+// Narrow-band streaming kernel ('N'): body in gbmv_systolic.cuh
 // ------------------------------------------------------------------------------------------------
-template <int W, int LDV>
-__device__ __forceinline__ void load_col(const double *__restrict__ a, i64 lda, i64 c, bool valid, double (&col)[W])
-{
-    if (LDV == 8) {
-        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (valid) {
-            ld_stream_v4(a + c * 8, v[0], v[1], v[2], v[3]);
-            if (W > 4) ld_stream_v4(a + c * 8 + 4, v[4], v[5], v[6], v[7]);
-        }
-#pragma unroll
-        for (int r = 0; r < W; ++r) col[r] = v[r];
-    } else if (LDV == 4) {
-        double v[4] = {0, 0, 0, 0};
-        if (valid) ld_stream_v4(a + c * 4, v[0], v[1], v[2], v[3]);
-#pragma unroll
-        for (int r = 0; r < W; ++r) col[r] = v[r];
-    } else if (LDV == 2) {
-        double v[2] = {0, 0};
-        if (valid) ld_stream_v2(a + c * 2, v[0], v[1]);
-#pragma unroll
-        for (int r = 0; r < W; ++r) col[r] = v[r];
-    } else {
-        const double *p = a + c * lda;
-#pragma unroll
-        for (int r = 0; r < W; ++r) col[r] = valid ? ld_stream(p + r) : 0.0;
-    }
-}
-
-// Virtual columns 0 .. m+ku-1 are cut into sets of 32 and runs of `sets_per_run` sets; run q is
-// processed by warp (q mod nwarps).  Rows completed by a run: [cs-ku, ce-ku).
 template <int W, int LDV>
 __global__ void __launch_bounds__(256)
 gbmv_n_systolic(i64 m, i64 n, int kl, int ku, double alpha, const double *__restrict__ a, i64 lda,
                 const double *__restrict__ x, double beta, double *__restrict__ y, i64 total_sets,
                 i64 sets_per_run, i64 num_runs)
 {
-    const int lane = threadIdx.x & 31;
-    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
-    const bool bz = (beta == 0.0);
-    const int src = (lane + 31) & 31;
-
-    for (i64 run = warp; run < num_runs; run += nwarps) {
-        const i64 set0 = run * sets_per_run;
-        const i64 set1 = (set0 + sets_per_run < total_sets) ? set0 + sets_per_run : total_sets;
-        const i64 cs = set0 * 32;
-
-        // ---- prologue: partial chains of the W-1 rows that started before column cs ----
-        double carry[W > 1 ? W - 1 : 1];
-        {
-            double part = 0.0;
-            if (lane < W - 1) {
-                const i64 i = cs + kl - 1 - lane;  // row entering lane 0 of the first set at step lane+1
-                if (i >= 0 && i < m) {
-                    part = bz ? 0.0 : __dmul_rn(beta, y[i]);
-                    i64 c0 = i - kl;
-                    if (c0 < 0) c0 = 0;
-                    i64 c1 = cs < n ? cs : n;
-                    for (i64 c = c0; c < c1; ++c)
-                        part = fma(__dmul_rn(alpha, x[c]), a[(ku + i - c) + c * lda], part);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < W - 1; ++s) carry[s] = shfl_d(part, s);
-        }
-
-        // ---- software-pipelined main loop: loads of set k+1 are in flight while set k is reduced ----
-        double col[W], ncol[W];
-        double xv, nxv, yin = 0.0, nyin = 0.0;
-        {
-            const i64 c = cs + lane;
-            const bool v = c < n;
-            load_col<W, LDV>(a, lda, c, v, col);
-            xv = v ? ld_stream(x + c) : 0.0;
-            if (!bz) yin = (c + kl < m) ? y[c + kl] : 0.0;
-        }
-        for (i64 set = set0; set < set1; ++set) {
-            const i64 c = set * 32 + lane;
-            if (set + 1 < set1) {
-                const i64 cn = c + 32;
-                const bool v = cn < n;
-                load_col<W, LDV>(a, lda, cn, v, ncol);
-                nxv = v ? ld_stream(x + cn) : 0.0;
-                if (!bz) nyin = (cn + kl < m) ? y[cn + kl] : 0.0;
-            }
-            const bool valid = c < n;
-            const double t = __dmul_rn(alpha, xv);
-            double acc = bz ? 0.0 : __dmul_rn(beta, yin);
-            if (valid) acc = fma(t, col[W - 1], acc);
-#pragma unroll
-            for (int s = 1; s < W; ++s) {
-                const double prev = carry[s - 1];
-                carry[s - 1] = acc;
-                const double in = shfl_d(lane == 31 ? prev : acc, src);
-                acc = valid ? fma(t, col[W - 1 - s], in) : in;
-            }
-            const i64 i = c - ku;
-            if (i >= 0 && i < m) st_stream(y + i, acc);
-#pragma unroll
-            for (int r = 0; r < W; ++r) col[r] = ncol[r];
-            xv = nxv;
-            yin = nyin;
-        }
-    }
+    gbmv_n_systolic_body<W, LDV, XPlain>(m, n, kl, ku, alpha, a, lda, XPlain{x}, beta, y, total_sets, sets_per_run,
+                                         num_runs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -226,22 +131,13 @@ template <int W, int LDV>
 static int launch_systolic(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double alpha, const double *dA, i64 lda,
                            const double *dx, double beta, double *dy)
 {
-    const i64 total_sets = cdiv64(m + ku, 32);
     const int threads = 256;
     int per_sm = 0;
     BMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gbmv_n_systolic<W, LDV>, threads, 0));
-    if (per_sm < 1) per_sm = 1;
-    i64 blocks = (i64)h->sm_count * per_sm;
-    i64 nwarps = blocks * (threads / 32);
-    // runs: an integer number k of runs per warp, about 96 sets (3072 columns) each
-    i64 k = total_sets / (nwarps * 96);
-    if (k < 1) k = 1;
-    i64 sets_per_run = cdiv64(total_sets, nwarps * k);
-    if (sets_per_run < 4) sets_per_run = 4;
-    const i64 num_runs = cdiv64(total_sets, sets_per_run);
-    if (num_runs < nwarps) blocks = cdiv64(num_runs, threads / 32);
-    gbmv_n_systolic<W, LDV><<<(unsigned)blocks, threads, 0, h->stream>>>(m, n, (int)kl, (int)ku, alpha, dA, lda, dx,
-                                                                         beta, dy, total_sets, sets_per_run, num_runs);
+    const SystolicPlan p = systolic_plan(m, ku, h->sm_count, per_sm, threads);
+    gbmv_n_systolic<W, LDV><<<(unsigned)p.blocks, threads, 0, h->stream>>>(m, n, (int)kl, (int)ku, alpha, dA, lda, dx,
+                                                                           beta, dy, p.total_sets, p.sets_per_run,
+                                                                           p.num_runs);
     BMB_LAUNCH_CHECK(h);
     return 0;
 }

@@ -18,7 +18,7 @@
 
 int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv);
 
-#define GBTRF_PF 4
+#define GBTRF_PF 12
 
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
 {
@@ -52,27 +52,34 @@ gbtrf_window(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i6
     __shared__ int s_jp;
     __shared__ int s_info;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nthr = blockDim.x;
+    // fixed (row, column-group) coordinates of this thread inside the window: no div/mod in the loop
+    const int ti = tid % (kl + 1), tc = tid / (kl + 1), tcs = nthr / (kl + 1);
+    const bool tact = tc < tcs;  // threads beyond the last full column group idle in (4b)
     const i64 mn = m < n ? m : n;
     const i64 ncols = (mn + kv < n) ? mn + kv : n;  // columns the factorisation can touch
-#define SLOT(c) (sm + (size_t)((c) % nslot) * ldw)
+#define SLOTI(s) (sm + (size_t)(s) * ldw)
 
     if (tid == 0) s_info = 0;
-    // initial window: columns 0 .. kv+PF-1
-    for (i64 c = 0; c < ncols && c < kv + GBTRF_PF; ++c) fetch_column(SLOT(c), ab, ldab, c, ldw, kl, kv);
+    // initial window: columns 0 .. kv+PF-1 (slot of column c is c mod nslot; nslot > kv+PF)
+    for (i64 c = 0; c < ncols && c < kv + GBTRF_PF; ++c) fetch_column(SLOTI((int)c), ab, ldab, c, ldw, kl, kv);
     cp_async_commit();
     cp_async_wait<0>();
 
-    i64 ju = 0;  // 0-based last column touched so far
+    i64 ju = 0;   // 0-based last column touched so far
+    int sj = 0;   // slot of column j
     for (i64 j = 0; j < mn; ++j) {
         const int km = (int)((kl < m - 1 - j) ? kl : (m - 1 - j));
         {   // (1) prefetch column j+kv+PF (its slot held column j-2, already written back)
             const i64 cf = j + kv + GBTRF_PF;
-            if (cf < ncols) fetch_column(SLOT(cf), ab, ldab, cf, ldw, kl, kv);
+            int sf = sj + kv + GBTRF_PF;
+            if (sf >= nslot) sf -= nslot;
+            if (cf < ncols) fetch_column(SLOTI(sf), ab, ldab, cf, ldw, kl, kv);
             cp_async_commit();
         }
         cp_async_wait<GBTRF_PF>();
         __syncthreads();  // (A) column j+kv landed; step j-1's updates are visible
-        double *colj = SLOT(j);
+        double *colj = SLOTI(sj);
         if (wid == 0) {  // (3) IDAMAX over rows j..j+km of column j: first maximum
             double best = -1.0;
             int bidx = 0;
@@ -91,9 +98,9 @@ gbtrf_window(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i6
                 ipiv[j] = j + bidx + 1;
             }
         } else if (j > 0) {  // write back the finished column j-1 while warp 0 searches
-            const double *src = SLOT(j - 1);
+            const double *src = SLOTI(sj == 0 ? nslot - 1 : sj - 1);
             double *dst = ab + (j - 1) * ldab;
-            for (int r = tid - 32; r < ldw; r += blockDim.x - 32) dst[r] = src[r];
+            for (int r = tid - 32; r < ldw; r += nthr - 32) dst[r] = src[r];
         }
         __syncthreads();  // (B)
         const int jp = s_jp;
@@ -105,43 +112,49 @@ gbtrf_window(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i6
             const int nc = (int)(ju - j);  // columns right of j that are touched
             const double rinv = 1.0 / pv;
             // (4a) stage the old pivot row, the old row j and the scaled multiplier column
-            for (int t = tid; t <= nc; t += blockDim.x) {
-                const double *s = SLOT(j + t);
+            for (int t = tid; t <= nc; t += nthr) {
+                int st = sj + t;
+                if (st >= nslot) st -= nslot;
+                const double *s = SLOTI(st);
                 urow[t] = s[kv + jp - t];
                 row0[t] = s[kv - t];
             }
-            for (int i = tid; i <= km; i += blockDim.x) {
+            for (int i = nthr - 1 - tid; i <= km; i += nthr) {  // from the far end: other warps than (4a)'s first loop
                 const double v = (i == jp) ? colj[kv] : colj[kv + i];
                 lcol[i] = (i == 0) ? pv : __dmul_rn(v, rinv);
             }
             __syncthreads();  // (C)
             // (4b) swap + scale + rank-1 update, every element touched by exactly one thread
-            const int items = (km + 1) * (nc + 1);
-            for (int t = tid; t < items; t += blockDim.x) {
-                const int i = t % (km + 1), c = t / (km + 1);
-                double *s = SLOT(j + c);
-                if (i == 0) s[kv - c] = urow[c];           // pivot row moves up (column 0: the pivot itself)
-                else if (c == 0) s[kv + i] = lcol[i];      // multipliers
-                else {
-                    const double aold = (i == jp) ? row0[c] : s[kv + i - c];
-                    s[kv + i - c] = fma(-urow[c], lcol[i], aold);
+            if (tact && ti <= km) {
+                const double li = lcol[ti];
+                for (int c = tc; c <= nc; c += tcs) {
+                    int sc = sj + c;
+                    if (sc >= nslot) sc -= nslot;
+                    double *s = SLOTI(sc);
+                    if (ti == 0) s[kv - c] = urow[c];          // pivot row moves up (column 0: the pivot itself)
+                    else if (c == 0) s[kv + ti] = li;          // multipliers
+                    else {
+                        const double aold = (ti == jp) ? row0[c] : s[kv + ti - c];
+                        s[kv + ti - c] = fma(-urow[c], li, aold);
+                    }
                 }
             }
         } else {
             if (tid == 0 && s_info == 0) s_info = (int)(j + 1);
         }
         // the barrier (A) of the next step orders (4b) before the next pivot search
+        sj = (sj + 1 == nslot) ? 0 : sj + 1;
     }
     cp_async_wait<0>();
     __syncthreads();
     // write back the last finished column and the touched-but-unfinished ones (n > m only)
     for (i64 c = (mn > 0 ? mn - 1 : 0); c < ncols && c <= mn - 1 + kv; ++c) {
-        const double *src = SLOT(c);
+        const double *src = SLOTI((int)(c % nslot));
         double *dst = ab + c * ldab;
-        for (int r = tid; r < ldw; r += blockDim.x) dst[r] = src[r];
+        for (int r = tid; r < ldw; r += nthr) dst[r] = src[r];
     }
     if (tid == 0) d_info[0] = s_info;
-#undef SLOT
+#undef SLOTI
 }
 
 extern "C" int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, double *dAB,
@@ -165,8 +178,10 @@ extern "C" int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl
     int rc;
     if (smem <= 220 * 1024) {
         BMB_CUDA(h, cudaFuncSetAttribute(gbtrf_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        i64 work = (kl + 1) * (kv + 1);
-        int threads = (int)imin64(1024, imax64(128, ((work + 31) / 32) * 32));
+        // (kl+1) x G threads, G column groups: one (row, column) element per thread when the window fits
+        i64 groups = imin64(kv + 1, 1024 / (kl + 1));
+        if (groups < 1) groups = 1;
+        int threads = (int)imin64(1024, imax64(128, (((kl + 1) * groups + 31) / 32) * 32));
         gbtrf_window<<<1, threads, smem, h->stream>>>(m, n, (int)kl, (int)ku, dAB, ldab, d_ipiv, h->d_info, nslot);
         BMB_LAUNCH_CHECK(h);
     } else {

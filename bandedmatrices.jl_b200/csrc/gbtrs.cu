@@ -111,62 +111,75 @@ gbtrs_n_kernel(i64 n, int kl, int ku, i64 nrhs, const double *__restrict__ ab, i
         for (int q = 0; q < nq; ++q)
             for (i64 r = lo + lane; r < n; r += 32) RG(q, r) = b[r + (c0 + q) * ldb];
         __syncwarp();
-        constexpr int KPU = 2 * KPL + 1;  // kv <= 2*kl.. callers guarantee 32*KPU >= kv
-        double U[KPU], Un[KPU], dg, dgn;
-        auto loadU = [&](i64 j, double (&dst)[KPU], double &d) {
+        constexpr int KPU = 2 * KPL + 1;  // callers guarantee 32*KPU >= kv
+        double U[SB][KPU], Un[SB][KPU], dg[SB], dgn[SB];
+        auto loadU = [&](i64 jtop, double (&dst)[SB][KPU], double (&d)[SB]) {  // steps jtop, jtop-1, ..., jtop-SB+1
 #pragma unroll
-            for (int k = 0; k < KPU; ++k) {
-                const int i = 1 + lane + 32 * k;  // distance above the diagonal
-                dst[k] = (j >= 0 && i <= kv && j - i >= 0) ? ab[(kv - i) + j * ldab] : 0.0;
+            for (int s = 0; s < SB; ++s) {
+                const i64 j = jtop - s;
+#pragma unroll
+                for (int k = 0; k < KPU; ++k) {
+                    const int i = 1 + lane + 32 * k;  // distance above the diagonal
+                    dst[s][k] = (j >= 0 && i <= kv && j - i >= 0) ? ab[(kv - i) + j * ldab] : 0.0;
+                }
+                d[s] = (j >= 0) ? ab[kv + j * ldab] : 1.0;
             }
-            d = (j >= 0) ? ab[kv + j * ldab] : 1.0;
         };
         loadU(n - 1, U, dg);
-        for (i64 j = n - 1; j >= 0; --j) {
-            loadU(j - 1, Un, dgn);
-            // window maintenance every 32 steps (counted from the top)
-            const i64 k = n - 1 - j;
-            if ((k & 31) == 0) {
-                if (k >= 32)
-                    for (int q = 0; q < nq; ++q) {
-                        const i64 r = j + 1 + lane;  // rows j+1 .. j+32 are final
-                        b[r + (c0 + q) * ldb] = RG(q, r);
+        for (i64 jtop = n - 1; jtop >= 0; jtop -= SB) {
+            loadU(jtop - SB, Un, dgn);
+#pragma unroll
+            for (int s = 0; s < SB; ++s) {
+                const i64 j = jtop - s;
+                if (j >= 0) {
+                    // window maintenance every 32 steps (counted from the bottom row)
+                    const i64 k = n - 1 - j;
+                    if ((k & 31) == 0) {
+                        if (k >= 32)
+                            for (int q = 0; q < nq; ++q) {
+                                const i64 r = j + 1 + lane;  // rows j+1 .. j+32 are final
+                                b[r + (c0 + q) * ldb] = RG(q, r);
+                            }
+                        __syncwarp();
+                        if (lo > 0) {
+                            const i64 nlo = (lo - 32 > 0) ? lo - 32 : 0;
+                            for (int q = 0; q < nq; ++q) {
+                                const i64 r = nlo + lane;
+                                if (r < lo) RG(q, r) = b[r + (c0 + q) * ldb];
+                            }
+                            lo = nlo;
+                        }
+                        __syncwarp();
                     }
-                __syncwarp();
-                if (lo > 0) {
-                    const i64 nlo = (lo - 32 > 0) ? lo - 32 : 0;
-                    for (int q = 0; q < nq; ++q) {
-                        const i64 r = nlo + lane;
-                        if (r < lo) RG(q, r) = b[r + (c0 + q) * ldb];
+                    double t[NR];
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) t[q] = RG(q, j) / dg[s];
+                    __syncwarp();
+                    if (lane < nq) {
+                        // lane q keeps its own quotient (all lanes computed all NR quotients identically)
+                        double mine = t[0];
+#pragma unroll
+                        for (int q = 1; q < NR; ++q) mine = (lane == q) ? t[q] : mine;
+                        RG(lane, j) = mine;
                     }
-                    lo = nlo;
-                }
-                __syncwarp();
-            }
-            double t[NR];
 #pragma unroll
-            for (int q = 0; q < NR; ++q) t[q] = RG(q, j) / dg;
-            __syncwarp();
-            if (lane < nq) {
-                // lane q keeps its own quotient (all lanes computed all NR quotients identically)
-                double mine = t[0];
+                    for (int kk = 0; kk < KPU; ++kk) {
+                        const int i = 1 + lane + 32 * kk;
+                        if (i <= kv && j - i >= 0) {
 #pragma unroll
-                for (int q = 1; q < NR; ++q) mine = (lane == q) ? t[q] : mine;
-                RG(lane, j) = mine;
-            }
-#pragma unroll
-            for (int kk = 0; kk < KPU; ++kk) {
-                const int i = 1 + lane + 32 * kk;
-                if (i <= kv && j - i >= 0) {
-#pragma unroll
-                    for (int q = 0; q < NR; ++q)
-                        if (q < nq) RG(q, j - i) = fma(-t[q], U[kk], RG(q, j - i));
+                            for (int q = 0; q < NR; ++q)
+                                if (q < nq) RG(q, j - i) = fma(-t[q], U[s][kk], RG(q, j - i));
+                        }
+                    }
+                    __syncwarp();
                 }
             }
-            __syncwarp();
 #pragma unroll
-            for (int kk = 0; kk < KPU; ++kk) U[kk] = Un[kk];
-            dg = dgn;
+            for (int s = 0; s < SB; ++s) {
+#pragma unroll
+                for (int kk = 0; kk < KPU; ++kk) U[s][kk] = Un[s][kk];
+                dg[s] = dgn[s];
+            }
         }
         // retire rows [0, first retired row)
         const i64 steps = n;                                   // steps executed
