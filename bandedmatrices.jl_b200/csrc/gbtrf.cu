@@ -157,6 +157,143 @@ gbtrf_window(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i6
 #undef SLOTI
 }
 
+// ------------------------------------------------------------------------------------------------
+// gbtrf_warp<NC>: one warp, everything in registers (kl <= 31, kl+ku+1 <= NC <= 64).
+//   lane = one ACTIVE ROW of the (kl+1)-row window, registers a[NC] = its entries in columns j..j+NC-1
+//   (column c lives in a[c % NC]; the step loop is unrolled NC-fold so every index is a constant).
+//   * IDAMAX  = three warp REDUX ops on the bit pattern of |v| (hi word, lo word, then min position => FIRST max)
+//   * DSWAP   = relabelling: rows never move between lanes, only their position numbers are exchanged
+//   * DSCAL   = v * (1/pivot); every lane computes the reciprocal of its own candidate while the REDUX chain runs
+//   * DGER    = pivot row published through shared memory, one FMA per (row, column): a = fma(-u, l, a)
+//   * the retired pivot row is the finished U row: written to AB by all lanes from shared memory; the freed lane
+//     picks up the next matrix row from a cp.async-fed ring of incoming columns.
+// No block barrier and no global latency on the chain of dependent pivot steps.
+// ------------------------------------------------------------------------------------------------
+#define GBW_PF 16
+
+template <int NC>
+__global__ void __launch_bounds__(32, 1)
+gbtrf_warp(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i64 *__restrict__ ipiv,
+           int *__restrict__ d_info)
+{
+    extern __shared__ double sm[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int kv = kl + ku, nb = kl + ku + 1;  // nb = original band rows per column
+    const int nring = NC + GBW_PF + 1;
+    double *ring = sm;                          // nring x nb : incoming columns (band rows kl..kl+kv of AB)
+    double *urow = sm + (size_t)nring * nb;     // NC        : the pivot row of the current step
+    const i64 mn = m < n ? m : n;
+    int info = 0;
+
+    auto fetch = [&](i64 c, int slot) {  // band part of column c -> ring[slot]
+        if (c < n)
+            for (int r = lane; r < nb; r += 32) cp_async8(ring + (size_t)slot * nb + r, ab + (kl + r) + c * ldab);
+    };
+    // entry (r, col) of the ORIGINAL matrix, read from the ring; zero outside the band / matrix
+    auto entry = [&](i64 r, i64 col, int slot) -> double {
+        const i64 d = (i64)ku + r - col;  // band row inside the nb rows
+        return (col < n && d >= 0 && d < nb) ? ring[(size_t)slot * nb + d] : 0.0;
+    };
+
+    for (int c = 0; c < NC + GBW_PF; ++c) fetch(c, c);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+
+    double a[NC];
+    i64 pos = (lane <= kl && lane < m) ? lane : -1;  // absolute row held by this lane, -1 = idle
+#pragma unroll
+    for (int c = 0; c < NC; ++c) a[c] = (pos >= 0) ? entry(pos, c, c) : 0.0;
+
+    int sj1 = 1;  // ring slot of column j+1
+    for (i64 jb = 0; jb < mn; jb += NC) {
+#pragma unroll
+        for (int ph = 0; ph < NC; ++ph) {
+            const i64 j = jb + ph;
+            if (j < mn) {
+                {   // keep the ring PF columns ahead of the entering row (which needs columns up to j+NC)
+                    int sf = sj1 + NC + GBW_PF - 1;  // slot of column j+NC+PF
+                    if (sf >= nring) sf -= nring;
+                    if (sf >= nring) sf -= nring;
+                    fetch(j + NC + GBW_PF, sf);
+                    cp_async_commit();
+                    cp_async_wait<GBW_PF>();
+                    __syncwarp();
+                }
+                const bool act = pos >= 0;
+                const double v = a[ph];
+                // ---- IDAMAX: first maximum of |v| over the active rows ----
+                const unsigned long long key = act ? (unsigned long long)__double_as_longlong(fabs(v)) : 0ull;
+                const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                const double rown = 1.0 / v;  // own reciprocal, overlapped with the reductions
+                const unsigned mhi = __reduce_max_sync(FULL, hi);
+                const bool c1 = act && hi == mhi;
+                const unsigned mlo = __reduce_max_sync(FULL, c1 ? lo : 0u);
+                const bool c2 = c1 && lo == mlo;
+                const unsigned rel = act ? (unsigned)(pos - j) : 0xffffffffu;
+                const int jp = (int)__reduce_min_sync(FULL, c2 ? rel : 0xffffffffu);
+                const int pl = __ffs(__ballot_sync(FULL, c2 && rel == (unsigned)jp)) - 1;  // pivot lane
+                const int lj = __ffs(__ballot_sync(FULL, act && rel == 0u)) - 1;           // lane holding row j
+                const double pv = shfl_d(v, pl);
+                const double rinv = shfl_d(rown, pl);
+                if (lane == 0) ipiv[j] = j + jp + 1;
+                if (pv == 0.0 && info == 0) info = (int)(j + 1);
+                // ---- DSWAP by relabelling ----
+                if (lane == lj) pos = j + jp;
+                if (lane == pl) pos = j;
+                // ---- publish the pivot row ----
+                if (lane == pl) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) urow[c] = a[(ph + c) % NC];
+                }
+                __syncwarp();
+                // ---- DSCAL + DGER (a zero pivot leaves the column untouched, like DGBTF2) ----
+                const bool upd = act && lane != pl;
+                const double l = (pv != 0.0) ? __dmul_rn(v, rinv) : v;
+                if (upd) ab[(kv + (pos - j)) + j * ldab] = l;
+#pragma unroll
+                for (int c = 1; c < NC; ++c) {
+                    const double u = urow[c];
+                    if (upd) a[(ph + c) % NC] = fma(-u, l, a[(ph + c) % NC]);
+                }
+                // ---- the finished U row goes out (all kv+1 entries: this also writes the fill-in zeros) ----
+                for (int c = lane; c < NC; c += 32)
+                    if (c <= kv && j + c < n) ab[(kv - c) + (j + c) * ldab] = urow[c];
+                // ---- the freed lane takes the next matrix row (columns j+1 .. j+NC) ----
+                const i64 rnew = j + kl + 1;
+                if (lane == pl) {
+                    if (rnew < m) {
+                        pos = rnew;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            int sl = sj1 + c;
+                            if (sl >= nring) sl -= nring;
+                            a[(ph + 1 + c) % NC] = entry(rnew, j + 1 + c, sl);
+                        }
+                    } else {
+                        pos = -1;
+                    }
+                }
+                __syncwarp();  // urow / ring slots are reused by the next step
+                sj1 = (sj1 + 1 == nring) ? 0 : sj1 + 1;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (lane == 0) d_info[0] = info;
+}
+
+template <int NC>
+static int launch_gbtrf_warp(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv)
+{
+    const size_t smem = ((size_t)(NC + GBW_PF + 1) * (kl + ku + 1) + NC) * sizeof(double);
+    BMB_CUDA(h, cudaFuncSetAttribute(gbtrf_warp<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gbtrf_warp<NC><<<1, 32, smem, h->stream>>>(m, n, (int)kl, (int)ku, dAB, ldab, d_ipiv, h->d_info);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
 extern "C" int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, double *dAB,
                              int64_t ldab, int64_t *d_ipiv, int *info)
 {
@@ -176,7 +313,15 @@ extern "C" int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl
     const int nslot = (int)(kv + GBTRF_PF + 2);
     const size_t smem = ((size_t)nslot * ldw + 2 * (kv + 1) + (kl + 1)) * sizeof(double);
     int rc;
-    if (smem <= 220 * 1024) {
+    if (kl <= 31 && kv + 1 <= 33) {  // register-resident single-warp kernel (wider windows spill a[] to local memory)
+        const i64 w = kv + 1;
+        if (w <= 4) rc = launch_gbtrf_warp<4>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
+        else if (w <= 8) rc = launch_gbtrf_warp<8>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
+        else if (w <= 16) rc = launch_gbtrf_warp<16>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
+        else if (w <= 24) rc = launch_gbtrf_warp<24>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
+        else rc = launch_gbtrf_warp<33>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
+        if (rc) return rc;
+    } else if (smem <= 220 * 1024) {
         BMB_CUDA(h, cudaFuncSetAttribute(gbtrf_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // (kl+1) x G threads, G column groups: one (row, column) element per thread when the window fits
         i64 groups = imin64(kv + 1, 1024 / (kl + 1));
