@@ -174,29 +174,46 @@ gbtrf_window(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i6
 template <int NC>
 __global__ void __launch_bounds__(32, 1)
 gbtrf_warp(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i64 *__restrict__ ipiv,
-           int *__restrict__ d_info)
+           int *__restrict__ d_info, int rmask)
 {
     extern __shared__ double sm[];
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int RP = (NC + 1) & ~1;  // ring row pitch (even => 16-byte aligned rows)
     const int lane = threadIdx.x;
-    const int kv = kl + ku, nb = kl + ku + 1;  // nb = original band rows per column
-    const int nring = NC + GBW_PF + 1;
-    double *ring = sm;                          // nring x nb : incoming columns (band rows kl..kl+kv of AB)
-    double *urow = sm + (size_t)nring * nb;     // NC        : the pivot row of the current step
+    const int kv = kl + ku, nb = kl + ku + 1;  // nb = original band entries per row / per column
+    // ring of incoming matrix ROWS (row-major, entries [0,nb) live, [nb,RP) permanently zero): the cp.async that
+    // fetches band column c scatters its entries to the rows they belong to, so an entering row is read back as
+    // contiguous doubles with no index arithmetic.
+    double *ring = sm;                                  // (rmask+1) x RP
+    double *urow = sm + (size_t)(rmask + 1) * RP;       // RP : the pivot row of the current step
     const i64 mn = m < n ? m : n;
     int info = 0;
 
-    auto fetch = [&](i64 c, int slot) {  // band part of column c -> ring[slot]
-        if (c < n)
-            for (int r = lane; r < nb; r += 32) cp_async8(ring + (size_t)slot * nb + r, ab + (kl + r) + c * ldab);
-    };
-    // entry (r, col) of the ORIGINAL matrix, read from the ring; zero outside the band / matrix
-    auto entry = [&](i64 r, i64 col, int slot) -> double {
-        const i64 d = (i64)ku + r - col;  // band row inside the nb rows
-        return (col < n && d >= 0 && d < nb) ? ring[(size_t)slot * nb + d] : 0.0;
+    for (int t = lane; t < (rmask + 1) * RP + RP; t += 32) sm[t] = 0.0;
+    __syncwarp();
+
+    // per-lane fetch state for band entries d = lane and d = lane+32 of the column being fetched (all incremental:
+    // no multiplications or 64-bit index arithmetic on the per-step path)
+    i64 fc = 0;                                           // next column to fetch
+    const bool has0 = lane < nb, has1 = lane + 32 < nb;
+    i64 fr0 = (i64)lane - ku, fr1 = (i64)lane + 32 - ku;  // matrix row of entry d in column fc
+    const double *fs0 = ab + (kl + lane), *fs1 = ab + (kl + lane + 32);
+    auto fetch = [&]() {  // entry (r, fc) lands at ring[(r & rmask)*RP + (kv - d)]
+        if (has0 && fr0 >= 0 && fr0 < m) {
+            double *dst = ring + ((int)fr0 & rmask) * RP + (kv - lane);
+            if (fc < n) cp_async8(dst, fs0);
+            else *dst = 0.0;  // virtual column right of the matrix
+        }
+        if (has1 && fr1 >= 0 && fr1 < m) {
+            double *dst = ring + ((int)fr1 & rmask) * RP + (kv - lane - 32);
+            if (fc < n) cp_async8(dst, fs1);
+            else *dst = 0.0;
+        }
+        ++fc; ++fr0; ++fr1;
+        fs0 += ldab; fs1 += ldab;
     };
 
-    for (int c = 0; c < NC + GBW_PF; ++c) fetch(c, c);
+    for (int c = 0; c < kv + 1 + GBW_PF; ++c) fetch();
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
@@ -204,23 +221,21 @@ gbtrf_warp(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i64 
     double a[NC];
     i64 pos = (lane <= kl && lane < m) ? lane : -1;  // absolute row held by this lane, -1 = idle
 #pragma unroll
-    for (int c = 0; c < NC; ++c) a[c] = (pos >= 0) ? entry(pos, c, c) : 0.0;
+    for (int c = 0; c < NC; ++c)  // row r = lane: column c sits at ring offset c - r + kl
+        a[c] = (pos >= 0 && c <= lane + ku && c < n) ? ring[lane * RP + (c - lane + kl)] : 0.0;
 
-    int sj1 = 1;  // ring slot of column j+1
+    double *pcol = ab + kv;                       // &AB(kv, j): diagonal slot of column j
+    const i64 ustride = ldab - 1;                 // U row j walks AB with this stride
+    const i64 uoff0 = (i64)lane * ustride, uoff1 = (i64)(lane + 32) * ustride;
     for (i64 jb = 0; jb < mn; jb += NC) {
 #pragma unroll
         for (int ph = 0; ph < NC; ++ph) {
             const i64 j = jb + ph;
             if (j < mn) {
-                {   // keep the ring PF columns ahead of the entering row (which needs columns up to j+NC)
-                    int sf = sj1 + NC + GBW_PF - 1;  // slot of column j+NC+PF
-                    if (sf >= nring) sf -= nring;
-                    if (sf >= nring) sf -= nring;
-                    fetch(j + NC + GBW_PF, sf);
-                    cp_async_commit();
-                    cp_async_wait<GBW_PF>();
-                    __syncwarp();
-                }
+                fetch();  // column j + kv + 1 + PF
+                cp_async_commit();
+                cp_async_wait<GBW_PF>();
+                __syncwarp();
                 const bool act = pos >= 0;
                 const double v = a[ph];
                 // ---- IDAMAX: first maximum of |v| over the active rows ----
@@ -249,34 +264,29 @@ gbtrf_warp(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i64 
                 }
                 __syncwarp();
                 // ---- DSCAL + DGER (a zero pivot leaves the column untouched, like DGBTF2) ----
-                const bool upd = act && lane != pl;
                 const double l = (pv != 0.0) ? __dmul_rn(v, rinv) : v;
-                if (upd) ab[(kv + (pos - j)) + j * ldab] = l;
+                if (act && lane != pl) pcol[(int)(pos - j)] = l;
+                const double2 *u2 = reinterpret_cast<const double2 *>(urow);
 #pragma unroll
-                for (int c = 1; c < NC; ++c) {
-                    const double u = urow[c];
-                    if (upd) a[(ph + c) % NC] = fma(-u, l, a[(ph + c) % NC]);
+                for (int c = 0; c < NC; c += 2) {  // idle / pivot lanes compute garbage that is never used
+                    const double2 u = u2[c >> 1];
+                    if (c >= 1) a[(ph + c) % NC] = fma(-u.x, l, a[(ph + c) % NC]);
+                    if (c + 1 < NC) a[(ph + c + 1) % NC] = fma(-u.y, l, a[(ph + c + 1) % NC]);
                 }
+                a[ph] = 0.0;  // this register now stands for column j+NC, structurally zero for every resident row
                 // ---- the finished U row goes out (all kv+1 entries: this also writes the fill-in zeros) ----
-                for (int c = lane; c < NC; c += 32)
-                    if (c <= kv && j + c < n) ab[(kv - c) + (j + c) * ldab] = urow[c];
-                // ---- the freed lane takes the next matrix row (columns j+1 .. j+NC) ----
+                if (lane <= kv && j + lane < n) pcol[uoff0] = urow[lane];
+                if (lane + 32 <= kv && j + lane + 32 < n) pcol[uoff1] = urow[lane + 32];
+                // ---- the freed lane takes the next matrix row (columns j+1 .. ; zeros beyond its band) ----
                 const i64 rnew = j + kl + 1;
                 if (lane == pl) {
-                    if (rnew < m) {
-                        pos = rnew;
+                    pos = (rnew < m) ? rnew : -1;
+                    const double *src = ring + ((int)rnew & rmask) * RP;
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            int sl = sj1 + c;
-                            if (sl >= nring) sl -= nring;
-                            a[(ph + 1 + c) % NC] = entry(rnew, j + 1 + c, sl);
-                        }
-                    } else {
-                        pos = -1;
-                    }
+                    for (int c = 0; c < NC; ++c) a[(ph + 1 + c) % NC] = src[c];
                 }
-                __syncwarp();  // urow / ring slots are reused by the next step
-                sj1 = (sj1 + 1 == nring) ? 0 : sj1 + 1;
+                __syncwarp();  // urow / ring rows are reused by the next step
+                pcol += ldab;
             }
         }
     }
@@ -287,9 +297,11 @@ gbtrf_warp(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i64 
 template <int NC>
 static int launch_gbtrf_warp(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv)
 {
-    const size_t smem = ((size_t)(NC + GBW_PF + 1) * (kl + ku + 1) + NC) * sizeof(double);
+    int rows = 32;
+    while (rows < kl + ku + 1 + GBW_PF + 2) rows <<= 1;  // ring rows (power of two)
+    const size_t smem = ((size_t)rows + 1) * ((NC + 1) & ~1) * sizeof(double);
     BMB_CUDA(h, cudaFuncSetAttribute(gbtrf_warp<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gbtrf_warp<NC><<<1, 32, smem, h->stream>>>(m, n, (int)kl, (int)ku, dAB, ldab, d_ipiv, h->d_info);
+    gbtrf_warp<NC><<<1, 32, smem, h->stream>>>(m, n, (int)kl, (int)ku, dAB, ldab, d_ipiv, h->d_info, rows - 1);
     BMB_LAUNCH_CHECK(h);
     return 0;
 }

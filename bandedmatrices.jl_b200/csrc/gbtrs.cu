@@ -230,6 +230,134 @@ gbtrs_t_kernel(i64 n, int kl, int ku, i64 nrhs, const double *__restrict__ ab, i
         }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide bands (kl > 128): one CTA of 1024 threads per right-hand side, threads span the band, the active window of
+// b lives in a shared-memory ring, the L / U column of the next steps is prefetched into registers.
+// ------------------------------------------------------------------------------------------------
+#define GW_THREADS 1024
+#define GW_PF 4
+
+template <int KPL, int KPU>
+__global__ void __launch_bounds__(GW_THREADS, 1)
+gbtrs_wide_kernel(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab, const i64 *__restrict__ ipiv,
+                  double *__restrict__ b, i64 ldb, int ring)
+{
+    extern __shared__ double rg[];
+    const int tid = threadIdx.x, M = ring - 1;
+    const int kv = kl + ku;
+    double *x = b + (i64)blockIdx.x * ldb;
+#define RGW(row) rg[(int)(row) & M]
+    if (kl > 0) {
+        i64 hi = ((i64)kl + 2 * GW_THREADS < n) ? (i64)kl + 2 * GW_THREADS : n;  // rows [.., hi) resident
+        for (i64 r = tid; r < hi; r += GW_THREADS) RGW(r) = x[r];
+        __syncthreads();
+        double L[GW_PF][KPL];
+        auto loadL = [&](i64 j, double (&dst)[KPL]) {
+#pragma unroll
+            for (int k = 0; k < KPL; ++k) {
+                const int i = 1 + tid + GW_THREADS * k;
+                dst[k] = (j < n - 1 && i <= kl && j + i < n) ? ab[(kv + i) + j * ldab] : 0.0;
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < GW_PF; ++s) loadL(s, L[s]);
+        for (i64 j0 = 0; j0 < n - 1; j0 += GW_PF) {
+#pragma unroll
+            for (int s = 0; s < GW_PF; ++s) {
+                const i64 j = j0 + s;
+                if (j < n - 1) {
+                    if ((j & (GW_THREADS - 1)) == 0) {  // retire 1024 finished rows, pull 1024 new ones
+                        if (j >= GW_THREADS) x[j - GW_THREADS + tid] = RGW(j - GW_THREADS + tid);
+                        __syncthreads();
+                        if (hi < n) {
+                            if (hi + tid < n) RGW(hi + tid) = x[hi + tid];
+                            hi = (hi + GW_THREADS < n) ? hi + GW_THREADS : n;
+                        }
+                        __syncthreads();
+                    }
+                    const i64 p = ipiv[j] - 1;
+                    if (tid == 0 && p != j) { const double t0 = RGW(j); RGW(j) = RGW(p); RGW(p) = t0; }
+                    __syncthreads();
+                    const double t = -RGW(j);
+#pragma unroll
+                    for (int k = 0; k < KPL; ++k) {
+                        const int i = 1 + tid + GW_THREADS * k;
+                        if (i <= kl && j + i < n) RGW(j + i) = fma(t, L[s][k], RGW(j + i));
+                    }
+                    loadL(j + GW_PF, L[s]);  // refill this slot for step j+PF
+                    __syncthreads();
+                }
+            }
+        }
+        const i64 done = ((n - 2) >= 0) ? ((n - 2) & ~(i64)(GW_THREADS - 1)) : 0;
+        for (i64 r = done + tid; r < n; r += GW_THREADS) x[r] = RGW(r);
+        __syncthreads();
+    }
+    {
+        i64 lo = (n - ((i64)kv + 2 * GW_THREADS) > 0) ? n - ((i64)kv + 2 * GW_THREADS) : 0;
+        for (i64 r = lo + tid; r < n; r += GW_THREADS) RGW(r) = x[r];
+        __syncthreads();
+        double U[GW_PF][KPU], dg[GW_PF];
+        auto loadU = [&](i64 j, double (&dst)[KPU], double &d) {
+#pragma unroll
+            for (int k = 0; k < KPU; ++k) {
+                const int i = 1 + tid + GW_THREADS * k;
+                dst[k] = (j >= 0 && i <= kv && j - i >= 0) ? ab[(kv - i) + j * ldab] : 0.0;
+            }
+            d = (j >= 0) ? ab[kv + j * ldab] : 1.0;
+        };
+#pragma unroll
+        for (int s = 0; s < GW_PF; ++s) loadU(n - 1 - s, U[s], dg[s]);
+        for (i64 jt = n - 1; jt >= 0; jt -= GW_PF) {
+#pragma unroll
+            for (int s = 0; s < GW_PF; ++s) {
+                const i64 j = jt - s;
+                if (j >= 0) {
+                    const i64 k = n - 1 - j;
+                    if ((k & (GW_THREADS - 1)) == 0) {
+                        if (k >= GW_THREADS) x[j + 1 + tid] = RGW(j + 1 + tid);
+                        __syncthreads();
+                        if (lo > 0) {
+                            const i64 nlo = (lo - GW_THREADS > 0) ? lo - GW_THREADS : 0;
+                            if (nlo + tid < lo) RGW(nlo + tid) = x[nlo + tid];
+                            lo = nlo;
+                        }
+                        __syncthreads();
+                    }
+                    const double q = RGW(j) / dg[s];
+                    __syncthreads();
+                    if (tid == 0) RGW(j) = q;
+#pragma unroll
+                    for (int kk = 0; kk < KPU; ++kk) {
+                        const int i = 1 + tid + GW_THREADS * kk;
+                        if (i <= kv && j - i >= 0) RGW(j - i) = fma(-q, U[s][kk], RGW(j - i));
+                    }
+                    loadU(j - GW_PF, U[s], dg[s]);
+                    __syncthreads();
+                }
+            }
+        }
+        const i64 lastk = ((n - 1) & ~(i64)(GW_THREADS - 1));
+        const i64 top = n - 1 - lastk;
+        for (i64 r = tid; r <= ((lastk >= GW_THREADS) ? top : n - 1); r += GW_THREADS) x[r] = RGW(r);
+    }
+#undef RGW
+}
+
+template <int KPL, int KPU>
+static int launch_wide(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
+                       double *dB, i64 ldb)
+{
+    int ring = 4096;
+    while (ring < kl + ku + 1 + 3 * GW_THREADS) ring <<= 1;
+    const size_t smem = (size_t)ring * sizeof(double);
+    BMB_CUDA(h, cudaFuncSetAttribute(gbtrs_wide_kernel<KPL, KPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gbtrs_wide_kernel<KPL, KPU><<<(unsigned)nrhs, GW_THREADS, smem, h->stream>>>(n, (int)kl, (int)ku, dAB, ldab, d_ipiv,
+                                                                                 dB, ldb, ring);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
 template <int NR, int KPL, int SB>
 static int launch_n(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
                     double *dB, i64 ldb)
@@ -283,7 +411,10 @@ extern "C" int bmb200_dgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t k
                                          : launch_n<1, 1, 8>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
     if (need <= 2) return launch_n<2, 2, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
     if (need <= 4) return launch_n<2, 4, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    snprintf(h->err, sizeof(h->err), "dgbtrs: band (%lld,%lld) wider than (128, 288-kl) needs the wide-band solve kernel (not built yet)", (long long)kl,
+    // wide bands: one CTA per right-hand side
+    if (kl <= GW_THREADS && kl + ku <= 2 * GW_THREADS) return launch_wide<1, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    if (kl <= 2 * GW_THREADS && kl + ku <= 4 * GW_THREADS) return launch_wide<2, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    snprintf(h->err, sizeof(h->err), "dgbtrs: band (%lld,%lld) wider than (2048, 4096-kl) is not supported", (long long)kl,
              (long long)ku);
     return BMB200_ERR_CUDA;
 }
