@@ -21,6 +21,46 @@ def _time(fn, reps=5, setup=None):
     return best
 
 
+def laplacian(bm, N):
+    """examples/finitedifference_2d.jl: A = I - dt*Laplacian_2D, dt = 1/(4 N^2): diag 2, +-1 and +-N bands -0.25."""
+    n = N * N
+    A = bm.BandedMatrix.zeros((n, n), (N, N))
+    d = A.data  # (n, 2N+1): d[j, r] = band row r of column j
+    d[:, N] = 2.0
+    j = torch.arange(n, device=d.device)
+    d[1:, N - 1] = torch.where(j[1:] % N != 0, -0.25, 0.0).to(d.dtype)
+    d[:-1, N + 1] = torch.where((j[:-1] + 1) % N != 0, -0.25, 0.0).to(d.dtype)
+    d[N:, 0] = -0.25
+    d[:-N, 2 * N] = -0.25
+    return A
+
+
+def run_c5(bm, N=1024):
+    n = N * N
+    A = laplacian(bm, N)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    F = bm.lu(A)
+    b.record()
+    b.synchronize()
+    t_f = a.elapsed_time(b)
+    rhs = torch.ones(n, dtype=torch.float64, device="cuda")
+    x = rhs.clone()
+    a.record()
+    bm.ldiv_(F, x)
+    b.record()
+    b.synchronize()
+    t_s = a.elapsed_time(b)
+    r = rhs.clone()
+    bm.mul_(r, A, x, -1.0, 1.0)
+    res = float(r.abs().max() / x.abs().max())
+    ident = bool((torch.as_tensor(F.ipiv) == torch.arange(1, n + 1)).all())
+    flops = 2.0 * n * N * N + n * N
+    return {"N": N, "n": n, "lu_ms_incl_widen": round(t_f, 1), "lu_TFLOPs": round(flops / t_f / 1e9, 3), "solve_ms": round(t_s, 1),
+            "pivots_identity": ident, "max_residual_over_max_x": res}
+
+
 def run_extras(bm, c3_n=1 << 22, c4_n=1 << 20, c4_rhs=256):
     out = {}
     # ---- C1 ----
@@ -72,4 +112,7 @@ def run_extras(bm, c3_n=1 << 22, c4_n=1 << 20, c4_rhs=256):
     out["C4"] = {"n": n, "nrhs": nrhs, "gbtrf_ms": round(t_f, 2), "gbtrf_ns_per_column": round(1e6 * t_f / n, 1),
                  "nontrivial_pivots": nontrivial, "gbtrs_ms": round(t_s, 2), "gbtrs_GFLOPs": round(fl_s / t_s / 1e6, 1),
                  "gbtrs_GBs": round(by_s / t_s / 1e6, 1), "gbtrs_hbm_roofline_ms": round(by_s / 6531.9e6, 3)}
+    del F, X, Bm, W, A
+    torch.cuda.empty_cache()
+    out["C5"] = run_c5(bm, 1024)
     return out

@@ -1,0 +1,123 @@
+# BandedMatricesB200.jl -- Julia glue for libbmb200 (include/bmb200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY: the build image has no Julia.  It is the literal binding a maintainer adds next to
+# BandedMatrices.jl; every method shadows one call site of the reference (cited) with a `ccall` into the C ABI.
+# The same ABI is exercised end to end by the Python host mirror (bandedmatrices.jl_b200/) and tests/.
+module BandedMatricesB200
+
+using LinearAlgebra, BandedMatrices, ArrayLayouts
+import LinearAlgebra: BlasInt, LAPACK
+import BandedMatrices: banded_gbmv!, _gbmm!, bandeddata, bandwidth, BandedMatrix, _BandedMatrix
+
+const libbmb200 = get(ENV, "LIBBMB200", "libbmb200.so")
+const Handle = Ptr{Cvoid}
+const HANDLE = Ref{Handle}(C_NULL)
+
+function handle()
+    if HANDLE[] == C_NULL
+        rc = ccall((:bmb200_create, libbmb200), Cint, (Ref{Handle}, Cint, Ptr{Cvoid}), HANDLE, 0, C_NULL)
+        rc == 0 || error("bmb200_create failed ($rc): no sm_100a GPU; there is no CPU fallback")
+    end
+    HANDLE[]
+end
+chk(rc, what) = rc == 0 ? nothing :
+    rc < 0 && rc > -100 ? throw(ArgumentError("invalid argument #$(-rc) to $what")) :
+    error("$what failed: " * unsafe_string(ccall((:bmb200_last_error, libbmb200), Cstring, (Handle,), handle())))
+
+# ---- device array: the container type that routes BandedMatrix to the BLAS layouts (BandedMatrix.jl:37-41) ----
+mutable struct B200Array{T,N} <: DenseArray{T,N}
+    ptr::Ptr{T}
+    dims::NTuple{N,Int}
+    function B200Array{T,N}(::UndefInitializer, dims::NTuple{N,Int}) where {T,N}
+        p = Ref{Ptr{Cvoid}}()
+        chk(ccall((:bmb200_malloc, libbmb200), Cint, (Handle, Ref{Ptr{Cvoid}}, Csize_t), handle(), p, sizeof(T) * prod(dims)), "malloc")
+        a = new{T,N}(Ptr{T}(p[]), dims)
+        finalizer(x -> ccall((:bmb200_free, libbmb200), Cint, (Handle, Ptr{Cvoid}), handle(), x.ptr), a)
+    end
+end
+Base.size(a::B200Array) = a.dims
+Base.strides(a::B200Array{T,2}) where {T} = (1, a.dims[1])
+Base.unsafe_convert(::Type{Ptr{T}}, a::B200Array{T}) where {T} = a.ptr
+Base.similar(a::B200Array{T}, ::Type{T}, dims::Dims{N}) where {T,N} = B200Array{T,N}(undef, dims)
+ArrayLayouts.MemoryLayout(::Type{<:B200Array}) = DenseColumnMajor()
+function B200Array(h::Array{T,N}) where {T,N}
+    d = B200Array{T,N}(undef, size(h))
+    chk(ccall((:bmb200_memcpy_h2d, libbmb200), Cint, (Handle, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), handle(), d.ptr, h, sizeof(h)), "h2d")
+    d
+end
+function Base.Array(d::B200Array{T,N}) where {T,N}
+    h = Array{T,N}(undef, d.dims)
+    chk(ccall((:bmb200_memcpy_d2h, libbmb200), Cint, (Handle, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), handle(), h, d.ptr, sizeof(h)), "d2h")
+    h
+end
+const DVec = B200Array{Float64,1}
+const DMat = B200Array{Float64,2}
+const DBanded = BandedMatrix{Float64,DMat}
+
+# ---- y <- alpha*op(A)*x + beta*y : shadows banded_gbmv! (src/generic/matmul.jl:21-23) ----
+function banded_gbmv!(tA, α, A::DBanded, x::DVec, β, y::DVec)
+    D = bandeddata(A)
+    chk(ccall((:bmb200_dgbmv, libbmb200), Cint,
+              (Handle, UInt8, Int64, Int64, Int64, Int64, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Int64),
+              handle(), tA, size(A, 1), size(D, 2), bandwidth(A, 1), bandwidth(A, 2), α, D, stride(D, 2), x, stride(x, 1), β, y, stride(y, 1)), "dgbmv")
+    y
+end
+
+# ---- C <- alpha*A*B + beta*C, banded x banded : shadows _gbmm! (src/banded/gbmm.jl:296-340) ----
+function _gbmm!(α::Float64, A_data::DMat, B_data::DMat, β, C_data::Union{DMat,SubArray{Float64,2,DMat}}, (n, ν, m), (Al, Au), (Bl, Bu), (Cl, Cu), Czero)
+    chk(ccall((:bmb200_dgbmm_bb, libbmb200), Cint,
+              (Handle, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Int64),
+              handle(), n, ν, m, Al, Au, Bl, Bu, Cl, Cu, α, A_data, stride(A_data, 2), B_data, stride(B_data, 2), β, pointer(C_data), stride(C_data, 2)), "dgbmm_bb")
+    C_data
+end
+
+# ---- banded x dense : shadows materialize!(MatMulMatAdd{<:BandedColumns,...}) (src/generic/matmul.jl:243-256) ----
+function ArrayLayouts.materialize!(M::ArrayLayouts.MatMulMatAdd{<:BandedMatrices.BandedColumns,<:Any,<:Any,Float64,<:DBanded,<:DMat,<:DMat})
+    A, B, C = M.A, M.B, M.C
+    D = bandeddata(A)
+    chk(ccall((:bmb200_dgbmm_bd, libbmb200), Cint,
+              (Handle, UInt8, Int64, Int64, Int64, Int64, Int64, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Int64),
+              handle(), 'N', size(A, 1), size(A, 2), bandwidth(A, 1), bandwidth(A, 2), size(B, 2), M.α, D, stride(D, 2), B, stride(B, 2), M.β, C, stride(C, 2)), "dgbmm_bd")
+    C
+end
+
+# ---- _fill_lmul! / zero! on device blocks (src/generic/utils.jl:29-31) ----
+function LinearAlgebra.lmul!(β::Number, C::DMat)
+    chk(ccall((:bmb200_dfill_lmul, libbmb200), Cint, (Handle, Float64, Ptr{Float64}, Int64, Int64, Int64, Int64),
+              handle(), β, C, size(C, 1), size(C, 2), stride(C, 2), 1), "dfill_lmul")
+    C
+end
+ArrayLayouts.zero!(C::DMat) = lmul!(0.0, C)
+
+# ---- lu: widening copy (src/banded/BandedLU.jl:108-111) + gbtrf! (BandedLU.jl:98) ----
+function BandedMatrix{Float64}(A::DBanded, (l, u2)::NTuple{2,Integer})   # only the (l, l+u) widening used by _lu
+    l0, u0 = bandwidths(A)
+    @assert l == l0 && u2 == l0 + u0
+    W = _BandedMatrix(DMat(undef, (2l0 + u0 + 1, size(A, 2))), size(A, 1), l0, l0 + u0)
+    chk(ccall((:bmb200_dband_widen, libbmb200), Cint, (Handle, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+              handle(), size(A, 2), l0, u0, bandeddata(A), stride(bandeddata(A), 2), bandeddata(W), stride(bandeddata(W), 2)), "dband_widen")
+    W
+end
+
+const DEVICE_IPIV = IdDict{Any,B200Array{Int64,1}}()   # device mirror of BandedLU.ipiv, keyed by the host vector
+
+function LAPACK.gbtrf!(kl::Integer, ku::Integer, m::Integer, AB::DMat)
+    n = size(AB, 2)
+    dip = B200Array{Int64,1}(undef, (min(m, n),))
+    info = Ref{Cint}(0)
+    chk(ccall((:bmb200_dgbtrf, libbmb200), Cint, (Handle, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Ref{Cint}),
+              handle(), m, n, kl, ku, AB, stride(AB, 2), dip, info), "dgbtrf")
+    LAPACK.chklapackerror(BlasInt(info[]))           # info > 0 -> LAPACKException, as the stdlib wrapper does
+    ipiv = Array(dip)                                 # BandedLU.ipiv is a host Vector{Int64} (BandedLU.jl:12)
+    DEVICE_IPIV[ipiv] = dip
+    AB, ipiv
+end
+
+function LAPACK.gbtrs!(trans::AbstractChar, kl::Integer, ku::Integer, m::Integer, AB::DMat, ipiv::Vector{BlasInt}, B::Union{DVec,DMat})
+    dip = get!(() -> B200Array(ipiv), DEVICE_IPIV, ipiv)
+    chk(ccall((:bmb200_dgbtrs, libbmb200), Cint, (Handle, UInt8, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}, Int64),
+              handle(), trans, size(AB, 2), kl, ku, size(B, 2), AB, stride(AB, 2), dip, B, max(1, stride(B, 2))), "dgbtrs")
+    B
+end
+
+end # module
