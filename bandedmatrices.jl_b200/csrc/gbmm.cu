@@ -17,12 +17,12 @@
 __global__ void __launch_bounds__(256)
 gbmm_bb_sweep(i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 Cu, double alpha,
               const double *__restrict__ a, i64 lda, const double *__restrict__ b, i64 ldb, double beta,
-              double *__restrict__ c, i64 ldc)
+              double *__restrict__ c, i64 ldc, i64 jbeg)
 {
     const int lane = threadIdx.x & 31;
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
-    for (i64 j = warp; j < m; j += nwarps) {
+    for (i64 j = jbeg + warp; j < m; j += nwarps) {
         i64 k0 = j - Cu; if (k0 < 0) k0 = 0;
         i64 k1 = j + Cl; if (k1 > n - 1) k1 = n - 1;
         // columns right of every B column that meets A (j >= nu+Bu): the reference beta-fills the WHOLE band
@@ -51,6 +51,127 @@ gbmm_bb_sweep(i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// gbmm_bb_dmma: banded x banded on the FP64 tensor cores (DMMA.8x8x4), for band widths whose tiles are dense
+// enough.  In band storage every in-band tile is column-major dense with pitch lda-1, so C[K,J] += A[K,V] * B[V,J]
+// over 8x8 (K,J) tiles and 4-wide V steps.  A CTA owns TJ output columns: the A columns [j0-Bu, j0+TJ+Bl) and the
+// (alpha-scaled) B columns are staged once in shared memory with zero pads above/below each column, so out-of-band
+// fragment elements read as 0.0 with no per-element test.  Column pitches are = 5 (mod 16) doubles, which makes
+// both fragment loads (A: lane -> (row l/4, k l%4); B: lane -> (k l%4, col l/4)) bank-conflict free.
+// DMMA.8x8x4 was verified on this GPU to equal the sequential FMA chain over k (tools/fp64_peaks.cu), and V is
+// walked in ascending order from beta*C, so the result is bit-identical to the reference's per-column dgbmv_ chain.
+// ------------------------------------------------------------------------------------------------
+#define GM_TJ 32          // output columns per CTA
+#define GM_NT 9           // row tiles (of 8) per work item  => 18 accumulator doubles per lane
+#define GM_PAD 11         // zero pad (doubles) above and below every staged column
+#define GM_THREADS 256
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__host__ __device__ __forceinline__ i64 floordiv(i64 a, i64 b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+__global__ void __launch_bounds__(GM_THREADS, 2)
+gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, int Cu, double alpha,
+             const double *__restrict__ a, i64 lda, const double *__restrict__ b, i64 ldb, double beta,
+             double *__restrict__ c, i64 ldc, int PA, int PB, int NA, i64 ntiles)
+{
+    extern __shared__ double sm[];
+    double *As = sm;                       // NA columns x PA
+    double *Bs = sm + (size_t)NA * PA;     // GM_TJ columns x PB
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int WA = Al + Au + 1, WB = Bl + Bu + 1;
+    // zero everything once: the pads are never written again
+    for (int t = tid; t < NA * PA + GM_TJ * PB; t += GM_THREADS) sm[t] = 0.0;
+    __syncthreads();
+    const int fr = lane >> 2, fk = lane & 3;   // fragment coordinates: A (row fr, k fk), B (k fk, col fr)
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const i64 j0 = tile * GM_TJ;
+        const i64 vbase = 4 * floordiv(j0 - Bu, 4);  // first staged A column (aligned to the k step)
+        // ---- stage A columns [vbase, vbase+NA) and B columns [j0, j0+TJ) ----
+        for (int s = wid; s < NA; s += GM_THREADS / 32) {
+            const i64 v = vbase + s;
+            double *dst = As + (size_t)s * PA + GM_PAD;
+            const double *src = a + v * lda;
+            for (int r = lane; r < WA; r += 32) {
+                const i64 k = v - Au + r;
+                dst[r] = (v >= 0 && v < nu && k >= 0 && k < n) ? src[r] : 0.0;
+            }
+        }
+        for (int s = wid; s < GM_TJ; s += GM_THREADS / 32) {
+            const i64 j = j0 + s;
+            double *dst = Bs + (size_t)s * PB + GM_PAD;
+            const double *src = b + j * ldb;
+            for (int r = lane; r < WB; r += 32) {
+                const i64 v = j - Bu + r;
+                dst[r] = (j < mcols && v >= 0 && v < nu) ? __dmul_rn(alpha, src[r]) : 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- work items: (column block of 8) x (chunk of GM_NT row tiles) ----
+        const i64 kfirst = 8 * floordiv(j0 - Cu, 8);                   // first row tile of column block 0
+        const int ntile_rows = (int)((Cu + Cl + 8 + 7 + 7) / 8);       // row tiles that can touch one column block
+        const int nchunks = (ntile_rows + GM_NT - 1) / GM_NT;
+        for (int item = wid; item < (GM_TJ / 8) * nchunks; item += GM_THREADS / 32) {
+            const int jb = item / nchunks, ch = item - jb * nchunks;
+            const i64 jc0 = j0 + 8 * jb;
+            if (jc0 >= mcols) continue;
+            const i64 k0 = kfirst + 8 * jb + (i64)8 * GM_NT * ch;      // first row of this chunk
+            const i64 k1 = k0 + 8 * GM_NT;                               // one past the last row
+            double acc[GM_NT][2];
+            // init = beta*C (or 0); lane owns C(k0 + 8t + fr, jc0 + 2*fk + {0,1})
+#pragma unroll
+            for (int t = 0; t < GM_NT; ++t) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const i64 k = k0 + 8 * t + fr, j = jc0 + 2 * fk + e;
+                    const bool in = (beta != 0.0) && j < mcols && k >= 0 && k < n && k - j <= Cl && j - k <= Cu;
+                    acc[t][e] = in ? __dmul_rn(beta, c[(Cu + k - j) + j * ldc]) : 0.0;
+                }
+            }
+            // V range: band of B over these columns, intersected with the band of A over these rows
+            i64 v0 = jc0 - Bu, v1 = jc0 + 7 + Bl;
+            if (v0 < k0 - Al) v0 = k0 - Al;
+            if (v1 > k1 - 1 + Au) v1 = k1 - 1 + Au;
+            if (v0 < 0) v0 = 0;
+            if (v1 > nu - 1) v1 = nu - 1;
+            v0 = 4 * floordiv(v0, 4);
+            const double *bcol = Bs + (size_t)(8 * jb + fr) * PB + GM_PAD + (Bu - (jc0 + fr));  // + v
+            for (i64 v = v0; v <= v1; v += 4) {
+                const double bf = bcol[v + fk];
+                const double *acol = As + (size_t)(v + fk - vbase) * PA + GM_PAD + (Au - (v + fk));  // + k
+#pragma unroll
+                for (int t = 0; t < GM_NT; ++t) {
+                    const i64 kt = k0 + 8 * t;
+                    if (kt + 7 >= v - Au && kt <= v + 3 + Al) {  // tile meets the band of A (warp-uniform)
+                        const double af = acol[kt + fr];
+                        dmma884(acc[t][0], acc[t][1], af, bf);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < GM_NT; ++t) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const i64 k = k0 + 8 * t + fr, j = jc0 + 2 * fk + e;
+                    if (j < mcols && k >= 0 && k < n && k - j <= Cl && j - k <= Cu) c[(Cu + k - j) + j * ldc] = acc[t][e];
+                }
+            }
+        }
+        __syncthreads();  // the staged columns are overwritten by the next tile
+    }
+}
+
+static int pitch5(int need)  // smallest p >= need with p = 5 (mod 16)
+{
+    int p = need;
+    while ((p & 15) != 5) ++p;
+    return p;
+}
+
 extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t m, int64_t Al, int64_t Au,
                                int64_t Bl, int64_t Bu, int64_t Cl, int64_t Cu, double alpha, const double *dA,
                                int64_t lda, const double *dB, int64_t ldb, double beta, double *dC, int64_t ldc)
@@ -72,10 +193,33 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
     if (!dC || (nu > 0 && (!dA || !dB))) return -12;
     DeviceGuard g(h->device);
     const int threads = 256;
-    const i64 blocks = imin64(cdiv64(m, threads / 32), (i64)h->sm_count * 8);
-    gbmm_bb_sweep<<<(unsigned)blocks, threads, 0, h->stream>>>(n, nu, m, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB,
-                                                               ldb, beta, dC, ldc);
-    BMB_LAUNCH_CHECK(h);
+    // columns j >= nu+Bu only get the beta-fill (whole band columns, like gbmm.jl:339): sweep kernel.
+    // The product columns go to the tensor-core kernel when the band is wide enough for dense tiles and the
+    // staged tiles fit in shared memory; otherwise to the sweep kernel as well.
+    i64 jsplit = 0;
+    const i64 mprod = imin64(m, nu + Bu);
+    const i64 WA = Al + Au + 1, WB = Bl + Bu + 1;
+    if (alpha != 0.0 && mprod > 0 && WA >= 9 && WB >= 9 && Cl == imin64(n - 1, Al + Bl) && Cu == imin64(m - 1, Au + Bu)) {
+        const int PA = pitch5((int)WA + 2 * GM_PAD), PB = pitch5((int)WB + 2 * GM_PAD);
+        const int NA = (int)(GM_TJ + Bl + Bu + 4 + 3);
+        const size_t smem = ((size_t)NA * PA + (size_t)GM_TJ * PB) * sizeof(double);
+        if (smem <= 110 * 1024) {
+            BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const i64 ntiles = cdiv64(mprod, GM_TJ);
+            const i64 blocks = imin64(ntiles, (i64)h->sm_count * 2);
+            gbmm_bb_dmma<<<(unsigned)blocks, GM_THREADS, smem, h->stream>>>(n, nu, mprod, (int)Al, (int)Au, (int)Bl, (int)Bu,
+                                                                         (int)Cl, (int)Cu, alpha, dA, lda, dB, ldb, beta,
+                                                                         dC, ldc, PA, PB, NA, ntiles);
+            BMB_LAUNCH_CHECK(h);
+            jsplit = mprod;
+        }
+    }
+    if (jsplit < m) {
+        const i64 blocks = imin64(cdiv64(m - jsplit, threads / 32), (i64)h->sm_count * 8);
+        gbmm_bb_sweep<<<(unsigned)blocks, threads, 0, h->stream>>>(n, nu, m, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB,
+                                                                   ldb, beta, dC, ldc, jsplit);
+        BMB_LAUNCH_CHECK(h);
+    }
     return 0;
 }
 
