@@ -179,3 +179,36 @@ def test_laplacian_lu_identity_pivots_and_residual(bm, oracle_ob, N):
     Ah = Band(data, n, N, N)
     oracle.gbmv(oracle_ob, "N", n, N, N, -1.0, data, x, 1.0, r)  # r = b - A x
     assert np.max(np.abs(r)) <= 1e-12 * np.max(np.abs(x)) * 3.0  # ||A||_inf = 3, cond ~ O(1)
+
+
+@pytest.mark.parametrize("shape", [(5000, 16, 16, 64), (3000, 16, 16, 40), (4097, 4, 3, 33), (2000, 5, 7, 16), (700, 32, 32, 32),
+                                   (1000, 31, 20, 17), (900, 0, 5, 32), (900, 6, 0, 32), (20, 4, 3, 32), (3, 2, 2, 16),
+                                   (257, 1, 1, 100), (1500, 2, 1, 64), (800, 20, 40, 24)])
+def test_solve_many_rhs_lane_kernel_bit_identical(bm, oracle_c, rng, shape):
+    """nrhs >= 16 and a narrow band: the one-lane-per-RHS register-window kernels (gbtrs_lane.cu).  Partial RHS tiles,
+    n smaller than the window / the prefetch distance, kl = 0 and ku = 0 included."""
+    n, l, u, nrhs = shape
+    A = brand(rng, n, n, l, u)
+    ab, ipiv, info = lu(oracle_c, A)
+    F = bm.lu(up(bm, A))
+    assert np.array_equal(F.ipiv, ipiv)
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    ref = B.copy(order="F")
+    ldiv(oracle_c, "N", ab, ipiv, l, u, ref)
+    X = bm.to_colmajor(B)
+    bm.ldiv_(F, X)
+    assert np.array_equal(X.cpu().numpy(), ref, equal_nan=True)
+
+
+def test_solve_many_rhs_c4_scaled_vs_openblas(bm, oracle_ob, rng):
+    """C4's band with 64 RHS at n = 2^15 against OpenBLAS dgbtrs itself."""
+    n, l, u, nrhs = 1 << 15, 16, 16, 64
+    A = brand(rng, n, n, l, u)
+    ab, ipiv, info = lu(oracle_ob, A)
+    F = bm.lu(up(bm, A))
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    ref = B.copy(order="F")
+    ldiv(oracle_ob, "N", ab, ipiv, l, u, ref)
+    X = bm.to_colmajor(B)
+    bm.ldiv_(F, X)
+    assert np.array_equal(X.cpu().numpy(), ref)
