@@ -15,8 +15,10 @@
 //                  merit is ns per column, not a roofline fraction.
 //   (wide bands: gbtrf_blocked.cu)
 #include "common.cuh"
+#include <stdlib.h>
 
 int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv);
+int bmb_gbtrf_reg(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv);  // gbtrf_reg.cu
 
 #define GBTRF_PF 12
 
@@ -325,7 +327,11 @@ extern "C" int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl
     const int nslot = (int)(kv + GBTRF_PF + 2);
     const size_t smem = ((size_t)nslot * ldw + 2 * (kv + 1) + (kl + 1)) * sizeof(double);
     int rc;
-    if (kl <= 31 && kv + 1 <= 33) {  // register-resident single-warp kernel (wider windows spill a[] to local memory)
+    static const bool old_warp = getenv("BMB200_GBTRF_OLD") != nullptr;  // development switch (A/B timing)
+    if (kl <= 31 && kv + 1 <= 33 && !old_warp) {  // software-pipelined register kernel (gbtrf_reg.cu)
+        rc = bmb_gbtrf_reg(h, m, n, kl, ku, dAB, ldab, d_ipiv);
+        if (rc) return rc;
+    } else if (kl <= 31 && kv + 1 <= 33) {  // first-generation register kernel
         const i64 w = kv + 1;
         if (w <= 4) rc = launch_gbtrf_warp<4>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
         else if (w <= 8) rc = launch_gbtrf_warp<8>(h, m, n, kl, ku, dAB, ldab, d_ipiv);

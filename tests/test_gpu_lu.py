@@ -212,3 +212,25 @@ def test_solve_many_rhs_c4_scaled_vs_openblas(bm, oracle_ob, rng):
     X = bm.to_colmajor(B)
     bm.ldiv_(F, X)
     assert np.array_equal(X.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("scale", [1e-300, 1e-160, 1e-30, 1e30, 1e150, 1e300])
+def test_solve_extreme_scaling_division_paths(bm, oracle_c, rng, scale):
+    """The backward sweep divides with a pre-refined reciprocal (divisor half hoisted off the dependency chain) and
+    falls back to the stock operator outside the fast path's range: wildly scaled factors and right-hand sides
+    (subnormal / huge quotients included) must still match DTBSV's true division bit for bit."""
+    n, l, u, nrhs = 600, 3, 2, 4
+    A = brand(rng, n, n, l, u)
+    A.data[:] = A.data * scale
+    ab, ipiv, info = lu(oracle_c, A)
+    F = bm.lu(up(bm, A))
+    assert np.array_equal(F.ipiv, ipiv)
+    assert np.array_equal(F.factors.banddata_host(), ab)
+    for bscale in (1.0, 1e-290, 1e290, 1e-308):
+        B = np.asfortranarray(rng.standard_normal((n, nrhs)) * bscale)
+        ref = B.copy(order="F")
+        with np.errstate(all="ignore"):
+            ldiv(oracle_c, "N", ab, ipiv, l, u, ref)
+        X = bm.to_colmajor(B)
+        bm.ldiv_(F, X)
+        assert np.array_equal(X.cpu().numpy(), ref, equal_nan=True), (scale, bscale)
