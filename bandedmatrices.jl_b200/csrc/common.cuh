@@ -73,6 +73,8 @@ int bmb_ensure_scratch(bmb200_ctx *h, size_t bytes);
 static inline i64 imin64(i64 a, i64 b) { return a < b ? a : b; }
 static inline i64 imax64(i64 a, i64 b) { return a > b ? a : b; }
 static inline i64 cdiv64(i64 a, i64 b) { return (a + b - 1) / b; }
+__device__ __forceinline__ i64 imin64_d(i64 a, i64 b) { return a < b ? a : b; }
+__device__ __forceinline__ i64 imax64_d(i64 a, i64 b) { return a > b ? a : b; }
 
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ double ld_stream(const double *p) {  // read-once data: bypass L1 allocation

@@ -68,11 +68,23 @@ gbmm_bb_sweep(i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
 }
 __host__ __device__ __forceinline__ i64 floordiv(i64 a, i64 b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// 8-byte asynchronous global->shared copy (LDGSTS); `valid == false` writes 0.0 without reading `src`
+__device__ __forceinline__ void cp_async8_zfill(double *dst, const double *src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(GM_THREADS, 2)
 gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, int Cu, double alpha,
@@ -88,76 +100,93 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
     for (int t = tid; t < NA * PA + GM_TJ * PB; t += GM_THREADS) sm[t] = 0.0;
     __syncthreads();
     const int fr = lane >> 2, fk = lane & 3;   // fragment coordinates: A (row fr, k fk), B (k fk, col fr)
+    const int ntile_rows = (Cu + Cl + 8 + 7 + 7) / 8;          // row tiles that can touch one column block
+    const int nchunks = (ntile_rows + GM_NT - 1) / GM_NT;
+    const unsigned span = (unsigned)(Al + Au + 10);
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const i64 j0 = tile * GM_TJ;
         const i64 vbase = 4 * floordiv(j0 - Bu, 4);  // first staged A column (aligned to the k step)
-        // ---- stage A columns [vbase, vbase+NA) and B columns [j0, j0+TJ) ----
+        // ---- stage A columns [vbase, vbase+NA) and B columns [j0, j0+TJ): asynchronous copies, all in flight ----
         for (int s = wid; s < NA; s += GM_THREADS / 32) {
             const i64 v = vbase + s;
             double *dst = As + (size_t)s * PA + GM_PAD;
-            const double *src = a + v * lda;
+            int rlo = 1, rhi = 0;  // band rows r with 0 <= v - Au + r < n
+            if (v >= 0 && v < nu) {
+                rlo = (v < Au) ? (int)(Au - v) : 0;
+                rhi = (int)imin64_d((i64)WA - 1, n - 1 - v + Au);
+            }
+            const double *src = a + (rlo <= rhi ? v * lda : 0);
             for (int r = lane; r < WA; r += 32) {
-                const i64 k = v - Au + r;
-                dst[r] = (v >= 0 && v < nu && k >= 0 && k < n) ? src[r] : 0.0;
+                const bool ok = r >= rlo && r <= rhi;
+                cp_async8_zfill(dst + r, ok ? src + r : a, ok);
             }
         }
         for (int s = wid; s < GM_TJ; s += GM_THREADS / 32) {
             const i64 j = j0 + s;
             double *dst = Bs + (size_t)s * PB + GM_PAD;
-            const double *src = b + j * ldb;
+            int rlo = 1, rhi = 0;  // band rows r with 0 <= j - Bu + r < nu
+            if (j < mcols) {
+                rlo = (j < Bu) ? (int)(Bu - j) : 0;
+                rhi = (int)imin64_d((i64)WB - 1, nu - 1 - j + Bu);
+            }
+            const double *src = b + (rlo <= rhi ? j * ldb : 0);
             for (int r = lane; r < WB; r += 32) {
-                const i64 v = j - Bu + r;
-                dst[r] = (j < mcols && v >= 0 && v < nu) ? __dmul_rn(alpha, src[r]) : 0.0;
+                const bool ok = r >= rlo && r <= rhi;
+                cp_async8_zfill(dst + r, ok ? src + r : b, ok);
             }
         }
+        cp_async_wait_all();
         __syncthreads();
-        // ---- work items: (column block of 8) x (chunk of GM_NT row tiles) ----
-        const i64 kfirst = 8 * floordiv(j0 - Cu, 8);                   // first row tile of column block 0
-        const int ntile_rows = (int)((Cu + Cl + 8 + 7 + 7) / 8);       // row tiles that can touch one column block
-        const int nchunks = (ntile_rows + GM_NT - 1) / GM_NT;
+        // ---- work items: (column block of 8) x (chunk of GM_NT row tiles); everything relative to j0 in int ----
+        const int kfirst_r = (int)(8 * floordiv(j0 - Cu, 8) - j0);     // first row tile of column block 0
+        const int vbase_r = (int)(vbase - j0);
         for (int item = wid; item < (GM_TJ / 8) * nchunks; item += GM_THREADS / 32) {
             const int jb = item / nchunks, ch = item - jb * nchunks;
-            const i64 jc0 = j0 + 8 * jb;
-            if (jc0 >= mcols) continue;
-            const i64 k0 = kfirst + 8 * jb + (i64)8 * GM_NT * ch;      // first row of this chunk
-            const i64 k1 = k0 + 8 * GM_NT;                               // one past the last row
+            const int jc0r = 8 * jb;
+            if (j0 + jc0r >= mcols) continue;
+            const int k0r = kfirst_r + 8 * jb + 8 * GM_NT * ch;        // first row of this chunk
             double acc[GM_NT][2];
             // init = beta*C (or 0); lane owns C(k0 + 8t + fr, jc0 + 2*fk + {0,1})
 #pragma unroll
             for (int t = 0; t < GM_NT; ++t) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const i64 k = k0 + 8 * t + fr, j = jc0 + 2 * fk + e;
-                    const bool in = (beta != 0.0) && j < mcols && k >= 0 && k < n && k - j <= Cl && j - k <= Cu;
-                    acc[t][e] = in ? __dmul_rn(beta, c[(Cu + k - j) + j * ldc]) : 0.0;
+                    const int kr = k0r + 8 * t + fr, jr = jc0r + 2 * fk + e;
+                    const i64 k = j0 + kr, j = j0 + jr;
+                    const bool in = (beta != 0.0) && j < mcols && k >= 0 && k < n && kr - jr <= Cl && jr - kr <= Cu;
+                    acc[t][e] = in ? __dmul_rn(beta, c[(Cu + kr - jr) + j * ldc]) : 0.0;
                 }
             }
-            // V range: band of B over these columns, intersected with the band of A over these rows
-            i64 v0 = jc0 - Bu, v1 = jc0 + 7 + Bl;
-            if (v0 < k0 - Al) v0 = k0 - Al;
-            if (v1 > k1 - 1 + Au) v1 = k1 - 1 + Au;
-            if (v0 < 0) v0 = 0;
-            if (v1 > nu - 1) v1 = nu - 1;
-            v0 = 4 * floordiv(v0, 4);
-            const double *bcol = Bs + (size_t)(8 * jb + fr) * PB + GM_PAD + (Bu - (jc0 + fr));  // + v
-            for (i64 v = v0; v <= v1; v += 4) {
-                const double bf = bcol[v + fk];
-                const double *acol = As + (size_t)(v + fk - vbase) * PA + GM_PAD + (Au - (v + fk));  // + k
+            // V range: band of B over these columns, intersected with the band of A over these rows and [0, nu)
+            int v0 = max(jc0r - Bu, k0r - Al), v1 = min(jc0r + 7 + Bl, k0r + 8 * GM_NT - 1 + Au);
+            if ((i64)v0 < -j0) v0 = (int)(-j0);
+            if ((i64)v1 > nu - 1 - j0) v1 = (int)(nu - 1 - j0);
+            v0 = (int)(4 * floordiv(j0 + v0, 4) - j0);                 // aligned like vbase
+            // B(v, j) -> Bs[jr*PB + PAD + v - jr + Bu];  A(k, v) -> As[(v - vbase)*PA + PAD + k - v + Au]
+            const double *bp = Bs + (size_t)(jc0r + fr) * PB + GM_PAD + Bu - (jc0r + fr) + fk + v0;
+            const double *ap = As + (size_t)(v0 + fk - vbase_r) * PA + GM_PAD + Au - (v0 + fk) + k0r + fr;
+            int d0 = k0r - v0 + Au + 7;   // tile t meets the band of A columns [v, v+3] iff 0 <= d0 + 8t <= span
+            const int astep = 4 * (PA - 1);
+            for (int v = v0; v <= v1; v += 4) {
+                const double bf = __dmul_rn(alpha, *bp);
 #pragma unroll
                 for (int t = 0; t < GM_NT; ++t) {
-                    const i64 kt = k0 + 8 * t;
-                    if (kt + 7 >= v - Au && kt <= v + 3 + Al) {  // tile meets the band of A (warp-uniform)
-                        const double af = acol[kt + fr];
+                    if ((unsigned)(d0 + 8 * t) <= span) {  // warp-uniform
+                        const double af = ap[8 * t];
                         dmma884(acc[t][0], acc[t][1], af, bf);
                     }
                 }
+                bp += 4;
+                ap += astep;
+                d0 -= 4;
             }
 #pragma unroll
             for (int t = 0; t < GM_NT; ++t) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const i64 k = k0 + 8 * t + fr, j = jc0 + 2 * fk + e;
-                    if (j < mcols && k >= 0 && k < n && k - j <= Cl && j - k <= Cu) c[(Cu + k - j) + j * ldc] = acc[t][e];
+                    const int kr = k0r + 8 * t + fr, jr = jc0r + 2 * fk + e;
+                    const i64 k = j0 + kr, j = j0 + jr;
+                    if (j < mcols && k >= 0 && k < n && kr - jr <= Cl && jr - kr <= Cu) c[(Cu + kr - jr) + j * ldc] = acc[t][e];
                 }
             }
         }

@@ -61,6 +61,21 @@ def test_gbmm_larger_and_star(bm, oracle_c, rng, shape):
     assert np.allclose(P.to_dense(), A.dense() @ B.dense(), rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("shape", [(3000, 3000, 3000, 32, 32, 32, 32), (2500, 2400, 2600, 40, 9, 12, 30), (1500, 1500, 1500, 8, 8, 8, 8),
+                                   (2100, 2000, 1900, 64, 64, 20, 20)])
+def test_gbmm_tensor_core_path_multi_tile(bm, oracle_c, rng, shape):
+    """Many column tiles per CTA on the DMMA kernel, alpha/beta both non-trivial: bit-identical to the per-column dgbmv_ replay."""
+    n, nu, m, Al, Au, Bl, Bu = shape
+    A, B = brand(rng, n, nu, Al, Au, corners=np.nan), brand(rng, nu, m, Bl, Bu, corners=np.nan)
+    Cl, Cu = min(n - 1, Al + Bl), min(m - 1, Au + Bu)
+    C0 = brand(rng, n, m, Cl, Cu)
+    ref = C0.data.copy(order="F")
+    gbmm_kernel(oracle_c, -0.75, A.data, B.data, 1.25, ref, n, nu, m, Al, Au, Bl, Bu, Cl, Cu)
+    Cm = up(bm, C0)
+    bm.mul_(Cm, up(bm, A), up(bm, B), -0.75, 1.25)
+    assert np.array_equal(Band(Cm.banddata_host(), n, Cl, Cu).dense(), Band(ref, n, Cl, Cu).dense())
+
+
 def test_gbmm_wider_C_and_banderror(bm, rng):
     """C with extra bands gets zeros/β-scaling there (test_broadcasting.jl:457-478); too few bands ⇒ BandError
     unless the missing bands are structurally zero (test_linalg.jl:272-295)."""

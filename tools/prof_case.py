@@ -23,3 +23,11 @@ elif what == "gbmm":
     for _ in range(2):
         bm.mul_(C, A, B)
     torch.cuda.synchronize()
+elif what == "widelu":
+    l = u = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    A = bm.brand(n, n, l, u, seed=5)
+    for _ in range(2):
+        F = bm.lu(A)
+        x = torch.ones(n, dtype=torch.float64, device="cuda")
+        bm.ldiv_(F, x)
+    torch.cuda.synchronize()
