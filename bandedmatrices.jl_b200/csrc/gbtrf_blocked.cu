@@ -200,6 +200,8 @@ gbtrf_update(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, co
     }
 }
 
+int bmb_gbtrf_pipe(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv, i64 *Jdone);
+
 int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv)
 {
     const i64 kv = kl + ku, mn = imin64(m, n);
@@ -231,8 +233,13 @@ int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, 
         gbtrf_zero_fill<<<blocks, 256, 0, h->stream>>>(n, kl, kv, dAB, ldab, ncols);
         BMB_LAUNCH_CHECK(h);
     }
+    // the bulk of the panels runs in the persistent pipelined kernel (gbtrf_pipe.cu); the stepwise kernels below
+    // finish the last kl/NB + 1 panels (ragged rows) or do everything when the shape is not eligible
+    i64 Jstart = 0;
+    rc = bmb_gbtrf_pipe(h, m, n, kl, ku, dAB, ldab, d_ipiv, &Jstart);
+    if (rc) return rc;
     const unsigned ublocks = (unsigned)cdiv64(kv, TC);
-    for (i64 J = 0; J < mn; J += NB) {
+    for (i64 J = Jstart; J < mn; J += NB) {
         const int nbw = (int)imin64(NB, n - J);
         gbtrf_panel<<<1, PANEL_THREADS, smem_p, h->stream>>>(m, n, (int)kl, (int)ku, dAB, ldab, d_ipiv, J, nbw, Lw, PR, st);
         h->launches++;
