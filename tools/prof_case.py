@@ -26,6 +26,8 @@ elif what == "gbmm":
 elif what == "widelu":
     l = u = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
     A = bm.brand(n, n, l, u, seed=5)
+    if len(sys.argv) > 4 and sys.argv[4] == "dom":
+        A.data[:, u] += 2.0 * (l + u + 1)
     for _ in range(2):
         F = bm.lu(A)
         x = torch.ones(n, dtype=torch.float64, device="cuda")

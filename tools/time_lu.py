@@ -12,6 +12,8 @@ import bandedmatrices_b200 as bm
 n, l, u, nrhs = (int(v) for v in sys.argv[1:5])
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 A = bm.brand(n, n, l, u, seed=4)
+if len(sys.argv) > 6 and sys.argv[6] == "dom":
+    A.data[:, u] += 2.0 * (l + u + 1)  # diagonally dominant: no interchanges
 ev = lambda: torch.cuda.Event(enable_timing=True)
 tf, ts = [], []
 for r in range(reps + 1):
