@@ -279,7 +279,11 @@ __device__ void gp_chain(const PipeArgs &A, double *smem)
     long long ju = 0, ju_prev = 0;
     int info = 0;
     long long tPf = 0, tCk = 0, tSt = 0, tCm = 0, tB = 0, tPub = 0, tWait = 0, tCp = 0, tTrsm = 0, tSchur = 0, tReload = 0, tRing = 0, t0 = 0, nblock = 0;
+#ifdef GP_PIPE_STATS   // development build: per-phase clock64 accounting by thread 0 (make NVFLAGS+=-DGP_PIPE_STATS)
 #define GP_TICK(acc) do { if (tid == 0) { const long long t1_ = clock64(); acc += t1_ - t0; t0 = t1_; } } while (0)
+#else
+#define GP_TICK(acc) do { } while (0)
+#endif
     if (tid == 0) t0 = clock64();
     // ---- panel 0 straight from AB ----
 #pragma unroll

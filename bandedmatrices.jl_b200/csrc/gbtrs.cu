@@ -16,7 +16,8 @@
 int bmb_gbtrs_lane(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
                    double *dB, i64 ldb);  // gbtrs_lane.cu
 int bmb_gbtrs_shfl(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
-                   double *dB, i64 ldb);  // gbtrs_shfl.cu
+                   double *dB, i64 ldb);
+int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb);  // gbtrs_shfl.cu
 
 // values per lane KPL = ceil(band/32); SB steps are prefetched together.
 template <int NR, int KPL, int SB>
@@ -424,7 +425,11 @@ extern "C" int bmb200_dgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t k
                                          : launch_n<1, 1, 8>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
     if (need <= 2) return launch_n<2, 2, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
     if (need <= 4) return launch_n<2, 4, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    // wide bands: one CTA per right-hand side
+    // wide bands: one CTA per right-hand side; interchange-free factors take the panel-blocked kernel (gbtrs_blocked.cu)
+    {
+        const int rc = bmb_gbtrs_blocked(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+        if (rc != 1) return rc;
+    }
     if (kl <= GW_THREADS && kl + ku <= 2 * GW_THREADS) return launch_wide<1, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
     if (kl <= 2 * GW_THREADS && kl + ku <= 4 * GW_THREADS) return launch_wide<2, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
     snprintf(h->err, sizeof(h->err), "dgbtrs: band (%lld,%lld) wider than (2048, 4096-kl) is not supported", (long long)kl,

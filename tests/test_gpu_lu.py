@@ -147,6 +147,41 @@ def test_wide_band_blocked_path_bit_identical_to_dgbtf2(bm, oracle_c, rng, shape
     assert np.array_equal(X.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("shape", [(2600, 300, 200, 3), (5000, 1024, 1024, 2), (1800, 150, 140, 1), (4100, 129, 500, 2)])
+def test_wide_band_dominant_optimistic_lu_and_blocked_solve(bm, oracle_c, rng, shape):
+    """Diagonally dominant wide bands (the C5 regime): the pipelined factorisation takes its optimistic path
+    (diagonal pivots, verified), the solve the panel-blocked interchange-free kernel.  Pivots = 1:n, factors and
+    solution bit-identical to DGBTF2 / DGBTRS."""
+    n, l, u, nrhs = shape
+    A = brand(rng, n, n, l, u)
+    A.data[u, :] += 2.0 * (l + u + 1)
+    ab, ipiv, info = lu(oracle_c, A)
+    assert np.array_equal(ipiv, np.arange(1, n + 1))
+    F = bm.lu(up(bm, A))
+    assert np.array_equal(F.ipiv, ipiv)
+    assert np.array_equal(F.factors.banddata_host(), ab)
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    ref = B.copy(order="F")
+    ldiv(oracle_c, "N", ab, ipiv, l, u, ref)
+    X = bm.to_colmajor(B)
+    bm.ldiv_(F, X)
+    assert np.array_equal(X.cpu().numpy(), ref)
+
+
+def test_wide_band_violation_mid_factorisation_falls_back(bm, oracle_c, rng):
+    """A dominant matrix with one weak diagonal far from the start: the optimistic path must notice, restore the panel
+    and continue with searched pivots -- still DGBTF2's pivots and bits."""
+    n, l, u = 3000, 200, 180
+    A = brand(rng, n, n, l, u)
+    A.data[u, :] += 2.0 * (l + u + 1)
+    A.data[u, 1777] = 1e-3          # forces an interchange at column 1777
+    ab, ipiv, info = lu(oracle_c, A)
+    assert (ipiv != np.arange(1, n + 1)).any()
+    F = bm.lu(up(bm, A))
+    assert np.array_equal(F.ipiv, ipiv)
+    assert np.array_equal(F.factors.banddata_host(), ab)
+
+
 def laplacian_band(N):
     """examples/finitedifference_2d.jl:10-16,29: A = I - dt*(kron(D2,I)+kron(I,D2)), D2 = N^2*tridiag(1,-2,1), dt = 1/(4N^2):
     diagonal 2, bands +-1 and +-N equal -0.25 (0 across block edges). Returns the (2N+1) x N^2 band data."""
