@@ -16,7 +16,39 @@
 #define GB_THREADS 1024
 #define GB_NB 16
 
-__device__ __forceinline__ void gb_prefetch_l2(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// TMA bulk prefetch of a contiguous range into L2 (UBLKPF.L2): the range is widened to 16-byte alignment
+__device__ __forceinline__ void gb_prefetch_l2_range(const double *p, int ndoubles)
+{
+    const unsigned long long a = (unsigned long long)p & ~15ull;
+    const unsigned bytes = (unsigned)((((unsigned long long)(p + ndoubles) + 15ull) & ~15ull) - a);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
+}
+
+// ---- correctly rounded x / d from a precomputed correctly rounded reciprocal ---------------------------------------
+// r = RN(1/d).  q0 = RN(x r) is within 2 ulp of x/d; one correction q1 = RN(q0 + (x - d q0) r) makes it faithful, and by
+// Markstein's theorem a second one, q2 = RN(q1 + (x - d q1) r) with the remainder exact in an FMA, is RN(x/d) -- provided
+// nothing over/underflows and d's significand is not all ones.  Those cases (and NaN/Inf/zero/subnormal operands) take
+// the IEEE division instead, so the result is the true quotient bit for bit in every case.
+__device__ __noinline__ double gb_div_ieee(double x, double d) { return x / d; }
+__device__ __forceinline__ bool gb_exp_mid(double v)  // 2^-500 <= |v| < 2^500 (excludes 0, subnormals, Inf, NaN)
+{
+    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+    return e - 523u <= 1000u;
+}
+__device__ __forceinline__ bool gb_div_safe_divisor(double d)
+{
+    const unsigned hi = (unsigned)__double2hiint(d) & 0xfffffu, lo = (unsigned)__double2loint(d);
+    return gb_exp_mid(d) && !(hi == 0xfffffu && lo == 0xffffffffu);
+}
+__device__ __forceinline__ double gb_div(double x, double d, double r, bool dsafe)
+{
+    if (dsafe && gb_exp_mid(x)) {
+        const double q0 = __dmul_rn(x, r);
+        const double q1 = fma(fma(-q0, d, x), r, q0);
+        return fma(fma(-q1, d, x), r, q1);
+    }
+    return gb_div_ieee(x, d);
+}
 
 __global__ void gbtrs_count_interchanges(i64 n, const i64 *__restrict__ ipiv, int *__restrict__ out)
 {
@@ -28,7 +60,7 @@ __global__ void gbtrs_count_interchanges(i64 n, const i64 *__restrict__ ipiv, in
 
 template <int KPL, int KPU>
 __global__ void __launch_bounds__(GB_THREADS, 1)
-gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab, double *__restrict__ b, i64 ldb, int ring)
+gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab, double *__restrict__ b, i64 ldb, int ring, int pfdist)
 {
     extern __shared__ double rg[];
     __shared__ double xs[GB_NB];
@@ -36,6 +68,14 @@ gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
     const int kv = kl + ku;
     constexpr int NB = GB_NB;
     double *x = b + (i64)blockIdx.x * ldb;
+#ifdef GB_STATS
+    long long cT[4] = {0, 0, 0, 0}, c0 = 0;
+#define GB_T0() do { if ((tid & 31) == 0) c0 = clock64(); } while (0)
+#define GB_T1(i) do { if ((tid & 31) == 0) cT[i] += clock64() - c0; } while (0)
+#else
+#define GB_T0() do { } while (0)
+#define GB_T1(i) do { } while (0)
+#endif
 #define RG(row) rg[(int)(row) & M]
     // =========================================== forward: L y = b ===========================================
     if (kl > 0) {
@@ -55,16 +95,16 @@ gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
         const i64 nblk = (n - kl >= NB) ? (n - kl) / NB : 0;
         // next panel's factor entries are pulled into L2 while this panel's triangle is solved: one 128-byte line per
         // thread (column jj = line / lpc holds kl contiguous doubles starting at L(J+NB, J+jj))
-        const int lpc = (kl * 8 + 127) / 128 + 1;  // lines per column, alignment slack included
-        auto prefetch_panel = [&](i64 J) {
-            for (int ln = tid; ln < NB * lpc; ln += GB_THREADS) {
-                const int jj = ln / lpc, off = (ln - jj * lpc) * 16;
-                if (off < kl + 16) gb_prefetch_l2(ab + (J + jj) * ldab + (kv + NB - jj) + (off < kl ? off : kl - 1));
+        auto prefetch_panel = [&](i64 J) {  // column J+jj from just below its diagonal (band row kv+1): triangle + rectangle
+            if (tid >= 32 && tid < 32 + NB) {
+                const int jj = tid - 32;
+                gb_prefetch_l2_range(ab + (J + jj) * ldab + (kv + 1), kl);
             }
         };
         for (i64 p = 0; p < nblk; ++p) {
             const i64 J = p * NB;
             if ((J & (GB_THREADS - 1)) == 0) window(J);
+            GB_T0();
             if (wid == 0) {  // 16 x 16 unit-lower triangle
                 double Lt[NB];
 #pragma unroll
@@ -76,10 +116,12 @@ gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
                     if (lane > jj) xi = fma(-u, Lt[jj], xi);
                 }
                 if (lane < NB) { RG(J + lane) = xi; xs[lane] = xi; }
-            } else if (p + 1 < nblk) {
-                prefetch_panel(J + NB);
+            } else if (pfdist > 0 && p + pfdist < nblk) {
+                prefetch_panel(J + (i64)pfdist * NB);
             }
+            GB_T1(0);
             __syncthreads();
+            GB_T0();
 #pragma unroll
             for (int k = 0; k < KPL; ++k) {
                 const int t = tid + GB_THREADS * k;
@@ -98,6 +140,7 @@ gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
                     RG(J + NB + t) = acc;
                 }
             }
+            GB_T1(1);
             __syncthreads();
         }
         // remaining columns one at a time
@@ -135,33 +178,46 @@ gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
         // blocked panels [J, J+NB), from the bottom; every row above exists (J >= kv)
         const i64 nblk = (n - kv >= NB) ? (n - kv) / NB : 0;
         // column J+jj holds the kv entries above its diagonal contiguously: U(J+jj-kv .. J+jj-1, J+jj) = band rows 0 .. kv-1
-        const int lpc = (kv * 8 + 127) / 128 + 1;
-        auto prefetch_panel = [&](i64 J) {
-            for (int ln = tid; ln < NB * lpc; ln += GB_THREADS) {
-                const int jj = ln / lpc, off = (ln - jj * lpc) * 16;
-                if (off < kv + 16) gb_prefetch_l2(ab + (J + jj) * ldab + (off < kv ? off : kv - 1));
+        auto prefetch_panel = [&](i64 J) {  // band rows 0 .. kv of column J+jj: rectangle, triangle and diagonal
+            if (tid >= 32 && tid < 32 + NB) {
+                const int jj = tid - 32;
+                gb_prefetch_l2_range(ab + (J + jj) * ldab, kv + 1);
             }
         };
         for (i64 p = 0; p < nblk; ++p) {
             const i64 J = n - (p + 1) * NB;
             if (((p * NB) & (GB_THREADS - 1)) == 0) window(J + NB - 1);
-            if (wid == 0) {  // 16 x 16 upper triangle, columns descending; true division by the diagonal
+            GB_T0();
+            if (wid == 0) {  // 16 x 16 upper triangle, columns descending; x / d correctly rounded (= true division)
+                const int i = lane & 15;
                 double Ut[NB];
+                {
+                    const double *pu = ab + J * ldab + (kv + i);  // U(J+i, J+jj) = pu[jj*(ldab-1)]
 #pragma unroll
-                for (int jj = 0; jj < NB; ++jj) Ut[jj] = (lane < NB && jj > lane && jj - lane <= kv) ? ab[(kv - (jj - lane)) + (J + jj) * ldab] : 0.0;
-                const double Ud = (lane < NB) ? ab[kv + (J + lane) * ldab] : 1.0;
-                double xi = (lane < NB) ? RG(J + lane) : 0.0;
+                    for (int jj = 0; jj < NB; ++jj) {
+                        Ut[jj] = (jj > i) ? *pu : 0.0;   // jj - i <= 15 <= kv: always inside the band
+                        pu += ldab - 1;
+                    }
+                }
+                const double Ud = ab[kv + (J + i) * ldab];
+                // One IEEE reciprocal per lane and panel, off the chain; each quotient on the chain is then two
+                // Markstein corrections (5 dependent FMAs instead of a 131-cycle division sequence) -- see gb_div.
+                const double rcp = 1.0 / Ud;
+                const bool dsafe = gb_div_safe_divisor(Ud);
+                double xi = RG(J + i);
 #pragma unroll
                 for (int jj = NB - 1; jj >= 0; --jj) {
-                    if (lane == jj) xi = xi / Ud;
+                    if (i == jj) xi = gb_div(xi, Ud, rcp, dsafe);
                     const double q = __shfl_sync(0xffffffffu, xi, jj);
-                    if (lane < jj) xi = fma(-q, Ut[jj], xi);
+                    if (i < jj) xi = fma(-q, Ut[jj], xi);
                 }
                 if (lane < NB) { RG(J + lane) = xi; xs[lane] = xi; }
-            } else if (p + 1 < nblk) {
-                prefetch_panel(J - NB);
+            } else if (pfdist > 0 && p + pfdist < nblk) {
+                prefetch_panel(J - (i64)pfdist * NB);
             }
+            GB_T1(2);
             __syncthreads();
+            GB_T0();
 #pragma unroll
             for (int k = 0; k < KPU; ++k) {
                 const int t = tid + GB_THREADS * k;  // row J - 1 - t
@@ -183,6 +239,7 @@ gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
                     RG(J - 1 - t) = acc;
                 }
             }
+            GB_T1(3);
             __syncthreads();
         }
         // remaining columns one at a time
@@ -203,6 +260,10 @@ gbtrs_wide_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
         const i64 top = n - 1 - lastk;
         for (i64 r = tid; r <= ((lastk >= GB_THREADS) ? top : n - 1); r += GB_THREADS) x[r] = RG(r);
     }
+#ifdef GB_STATS
+    if (blockIdx.x == 0 && (tid == 0 || tid == 32 || tid == 992))
+        printf("[gbtrs_blocked] tid %d cycles: fwd tri %lld rect %lld | bwd tri %lld rect %lld  (n=%lld)\n", tid, cT[0], cT[1], cT[2], cT[3], (long long)n);
+#endif
 #undef RG
 }
 
@@ -213,7 +274,8 @@ static int launch_noswap(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const d
     while (ring < kl + ku + 1 + 3 * GB_THREADS) ring <<= 1;
     const size_t smem = (size_t)ring * sizeof(double);
     BMB_CUDA(h, cudaFuncSetAttribute(gbtrs_wide_noswap<KPL, KPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gbtrs_wide_noswap<KPL, KPU><<<(unsigned)nrhs, GB_THREADS, smem, h->stream>>>(n, (int)kl, (int)ku, dAB, ldab, dB, ldb, ring);
+    static const int pfdist = getenv("BMB200_GBTRS_PFDIST") ? atoi(getenv("BMB200_GBTRS_PFDIST")) : 1;
+    gbtrs_wide_noswap<KPL, KPU><<<(unsigned)nrhs, GB_THREADS, smem, h->stream>>>(n, (int)kl, (int)ku, dAB, ldab, dB, ldb, ring, pfdist);
     BMB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -232,4 +294,23 @@ int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doub
     BMB_CUDA(h, cudaStreamSynchronize(h->stream));
     if (hc != 0) return 1;
     return launch_noswap<1, 2>(h, n, kl, ku, nrhs, dAB, ldab, dB, ldb);
+}
+
+// ---- test hook (not part of the public ABI): counts inputs where gb_div differs from the IEEE quotient ----
+__global__ void gb_divcheck_kernel(i64 n, const double *__restrict__ x, const double *__restrict__ d, unsigned long long *__restrict__ bad)
+{
+    for (i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x; t < n; t += (i64)gridDim.x * blockDim.x) {
+        const double dv = d[t], xv = x[t];
+        const double r = 1.0 / dv;
+        const double q = gb_div(xv, dv, r, gb_div_safe_divisor(dv)), ref = xv / dv;
+        if (__double_as_longlong(q) != __double_as_longlong(ref) && !(q != q && ref != ref)) atomicAdd(bad, 1ull);
+    }
+}
+extern "C" int bmb200_internal_divcheck(bmb200_handle_t h, int64_t n, const double *dx, const double *dd, unsigned long long *dbad)
+{
+    if (!h) return -1;
+    DeviceGuard g(h->device);
+    gb_divcheck_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(n, dx, dd, dbad);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
 }

@@ -269,3 +269,35 @@ def test_solve_extreme_scaling_division_paths(bm, oracle_c, rng, scale):
         X = bm.to_colmajor(B)
         bm.ldiv_(F, X)
         assert np.array_equal(X.cpu().numpy(), ref, equal_nan=True), (scale, bscale)
+
+
+def test_blocked_solve_fast_division_is_the_ieee_quotient(bm, rng):
+    """gbtrs_blocked.cu replaces the per-column division of the back substitution by two Markstein corrections of
+    x * RN(1/d); the result must be the correctly rounded quotient bit for bit (DTBSV divides).
+    Random operands over the whole exponent range, near-powers-of-two, all-ones significands, zeros, subnormals, Inf."""
+    import ctypes as C
+
+    hd = bm.handle(0)
+    fn = hd.lib.bmb200_internal_divcheck
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = 1 << 24
+    m = rng.random(n) + 1.0
+    e = rng.integers(-1000, 1000, n)
+    x = np.ldexp(m, e) * rng.choice([-1.0, 1.0], n)
+    d = np.ldexp(rng.random(n) + 1.0, rng.integers(-1000, 1000, n)) * rng.choice([-1.0, 1.0], n)
+    # adversarial significands
+    k = n // 16
+    d[:k] = np.ldexp(2.0 - 2.0 ** -52, rng.integers(-600, 600, k))            # all ones
+    d[k:2 * k] = np.ldexp(1.0 + 2.0 ** -52 * rng.integers(0, 4, k), rng.integers(-600, 600, k))
+    x[2 * k:3 * k] = np.ldexp(2.0 - 2.0 ** -52 * rng.integers(1, 4, k), rng.integers(-600, 600, k))
+    x[3 * k:3 * k + 8] = [0.0, -0.0, 5e-324, -1e-310, np.inf, -np.inf, np.nan, 1e-320]
+    d[4 * k:4 * k + 6] = [5e-324, 1e-310, np.inf, 1e308, 1e-308, 3.0]
+    # products that land near rounding boundaries: x = RN(q * d) for random q
+    q = np.ldexp(rng.random(k) + 1.0, rng.integers(-100, 100, k))
+    x[5 * k:6 * k] = q * d[5 * k:6 * k]
+    dx, dd = torch.as_tensor(x).cuda(), torch.as_tensor(d).cuda()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    hd.check(fn(hd.h, n, C.c_void_p(dx.data_ptr()), C.c_void_p(dd.data_ptr()), C.c_void_p(bad.data_ptr())), "divcheck")
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
