@@ -95,3 +95,30 @@ __device__ __forceinline__ void st_stream(double *p, double v) {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// ---- correctly rounded x / d from a precomputed correctly rounded reciprocal ---------------------------------------
+// r = RN(1/d).  q0 = RN(x r) is within 2 ulp of x/d; one correction q1 = RN(q0 + (x - d q0) r) makes it faithful, and by
+// Markstein's theorem a second one, q2 = RN(q1 + (x - d q1) r) with the remainder exact in an FMA, is RN(x/d) -- provided
+// nothing over/underflows and d's significand is not all ones.  Those cases (and NaN/Inf/zero/subnormal operands) take
+// the IEEE division instead, so the result is the true quotient bit for bit in every case.
+static __device__ __noinline__ double gb_div_ieee(double x, double d) { return x / d; }
+__device__ __forceinline__ bool gb_exp_mid(double v)  // 2^-500 <= |v| < 2^500 (excludes 0, subnormals, Inf, NaN)
+{
+    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+    return e - 523u <= 1000u;
+}
+__device__ __forceinline__ bool gb_div_safe_divisor(double d)
+{
+    const unsigned hi = (unsigned)__double2hiint(d) & 0xfffffu, lo = (unsigned)__double2loint(d);
+    return gb_exp_mid(d) && !(hi == 0xfffffu && lo == 0xffffffffu);
+}
+__device__ __forceinline__ double gb_div(double x, double d, double r, bool dsafe)
+{
+    if (dsafe && gb_exp_mid(x)) {
+        const double q0 = __dmul_rn(x, r);
+        const double q1 = fma(fma(-q0, d, x), r, q0);
+        return fma(fma(-q1, d, x), r, q1);
+    }
+    return gb_div_ieee(x, d);
+}
+
