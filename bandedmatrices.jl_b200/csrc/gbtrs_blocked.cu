@@ -254,11 +254,13 @@ static int launch_noswap(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const d
     return 0;
 }
 
+int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
+
 // returns 1 when not applicable (the caller then runs the general kernel), 0 on success, <0 on error
 int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb)
 {
     static const bool off = getenv("BMB200_GBTRS_NOBLOCK") != nullptr;
-    if (off || n < 4 * (kl + ku + GB_NB) || kl > GB_THREADS || kl + ku > 2 * GB_THREADS) return 1;
+    if (off) return 1;
     int *cnt = h->d_info + 16;
     BMB_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int), h->stream));
     gbtrs_count_interchanges<<<h->sm_count, 256, 0, h->stream>>>(n, d_ipiv, cnt);
@@ -267,6 +269,11 @@ int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doub
     BMB_CUDA(h, cudaMemcpyAsync(&hc, cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     BMB_CUDA(h, cudaStreamSynchronize(h->stream));
     if (hc != 0) return 1;
+    {   // one cluster per right-hand side, pipelined through distributed shared memory (gbtrs_cluster.cu)
+        const int rc = bmb_gbtrs_cluster(h, n, kl, ku, nrhs, dAB, ldab, dB, ldb);
+        if (rc != 1) return rc;
+    }
+    if (n < 4 * (kl + ku + GB_NB) || kl > GB_THREADS || kl + ku > 2 * GB_THREADS) return 1;
     return launch_noswap<1, 2>(h, n, kl, ku, nrhs, dAB, ldab, dB, ldb);
 }
 
