@@ -62,7 +62,6 @@ gbmm_bb_sweep(i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 
 // walked in ascending order from beta*C, so the result is bit-identical to the reference's per-column dgbmv_ chain.
 // ------------------------------------------------------------------------------------------------
 #define GM_TJ 32          // output columns per CTA
-#define GM_NT 9           // row tiles (of 8) per work item  => 18 accumulator doubles per lane
 #define GM_PAD 11         // zero pad (doubles) above and below every staged column
 #define GM_THREADS 256
 
@@ -86,6 +85,9 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// GM_NT = row tiles (of 8) per work item: the V range of an item is the union over its tiles, so a tall item spends
+// most of its predicated DMMA slots outside the band parallelogram (9 tiles: 44 % of the slots live; 3 tiles: 77 %).
+template <int GM_NT>
 __global__ void __launch_bounds__(GM_THREADS, 2)
 gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, int Cu, double alpha,
              const double *__restrict__ a, i64 lda, const double *__restrict__ b, i64 ldb, double beta,
@@ -116,9 +118,13 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
                 rhi = (int)imin64_d((i64)WA - 1, n - 1 - v + Au);
             }
             const double *src = a + (rlo <= rhi ? v * lda : 0);
-            for (int r = lane; r < WA; r += 32) {
-                const bool ok = r >= rlo && r <= rhi;
-                cp_async8_zfill(dst + r, ok ? src + r : a, ok);
+            if (rlo == 0 && rhi == WA - 1) {  // whole column inside the matrix (all but the first/last tiles)
+                for (int r = lane; r < WA; r += 32) cp_async8_zfill(dst + r, src + r, true);
+            } else {
+                for (int r = lane; r < WA; r += 32) {
+                    const bool ok = r >= rlo && r <= rhi;
+                    cp_async8_zfill(dst + r, ok ? src + r : a, ok);
+                }
             }
         }
         for (int s = wid; s < GM_TJ; s += GM_THREADS / 32) {
@@ -130,9 +136,13 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
                 rhi = (int)imin64_d((i64)WB - 1, nu - 1 - j + Bu);
             }
             const double *src = b + (rlo <= rhi ? j * ldb : 0);
-            for (int r = lane; r < WB; r += 32) {
-                const bool ok = r >= rlo && r <= rhi;
-                cp_async8_zfill(dst + r, ok ? src + r : b, ok);
+            if (rlo == 0 && rhi == WB - 1) {
+                for (int r = lane; r < WB; r += 32) cp_async8_zfill(dst + r, src + r, true);
+            } else {
+                for (int r = lane; r < WB; r += 32) {
+                    const bool ok = r >= rlo && r <= rhi;
+                    cp_async8_zfill(dst + r, ok ? src + r : b, ok);
+                }
             }
         }
         cp_async_wait_all();
@@ -146,15 +156,23 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
             if (j0 + jc0r >= mcols) continue;
             const int k0r = kfirst_r + 8 * jb + 8 * GM_NT * ch;        // first row of this chunk
             double acc[GM_NT][2];
-            // init = beta*C (or 0); lane owns C(k0 + 8t + fr, jc0 + 2*fk + {0,1})
+            // lane owns C(k0 + 8t + fr, jc0 + 2*fk + {0,1}) = cp0[8t + e*(ldc-1)]; rows and columns of an interior item are
+            // all inside the matrix, so only the band test remains (and none at all for a tile fully inside the band)
+            const bool inner = j0 + jc0r + 7 < mcols && j0 + k0r >= 0 && j0 + k0r + 8 * GM_NT - 1 < n;
+            double *cp0 = c + (Cu + (k0r + fr) - (jc0r + 2 * fk)) + (j0 + jc0r + 2 * fk) * ldc;
+            if (beta == 0.0) {
 #pragma unroll
-            for (int t = 0; t < GM_NT; ++t) {
+                for (int t = 0; t < GM_NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+            } else {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int kr = k0r + 8 * t + fr, jr = jc0r + 2 * fk + e;
-                    const i64 k = j0 + kr, j = j0 + jr;
-                    const bool in = (beta != 0.0) && j < mcols && k >= 0 && k < n && kr - jr <= Cl && jr - kr <= Cu;
-                    acc[t][e] = in ? __dmul_rn(beta, c[(Cu + kr - jr) + j * ldc]) : 0.0;
+                for (int t = 0; t < GM_NT; ++t) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int kr = k0r + 8 * t + fr, jr = jc0r + 2 * fk + e;
+                        const i64 k = j0 + kr, j = j0 + jr;
+                        const bool in = j < mcols && k >= 0 && k < n && kr - jr <= Cl && jr - kr <= Cu;
+                        acc[t][e] = in ? __dmul_rn(beta, cp0[8 * t + e * (ldc - 1)]) : 0.0;
+                    }
                 }
             }
             // V range: band of B over these columns, intersected with the band of A over these rows and [0, nu)
@@ -168,7 +186,7 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
             int d0 = k0r - v0 + Au + 7;   // tile t meets the band of A columns [v, v+3] iff 0 <= d0 + 8t <= span
             const int astep = 4 * (PA - 1);
             for (int v = v0; v <= v1; v += 4) {
-                const double bf = __dmul_rn(alpha, *bp);
+                const double bf = (alpha == 1.0) ? *bp : __dmul_rn(alpha, *bp);
 #pragma unroll
                 for (int t = 0; t < GM_NT; ++t) {
                     if ((unsigned)(d0 + 8 * t) <= span) {  // warp-uniform
@@ -180,17 +198,224 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
                 ap += astep;
                 d0 -= 4;
             }
+            if (inner) {
 #pragma unroll
-            for (int t = 0; t < GM_NT; ++t) {
+                for (int t = 0; t < GM_NT; ++t) {
+                    const int dlo = k0r + 8 * t - jc0r - 7, dhi = dlo + 14;  // row - column over the 8 x 8 tile
+                    if (dhi <= Cl && dlo >= -Cu) {                            // warp-uniform: tile fully inside the band
+                        cp0[8 * t] = acc[t][0];
+                        cp0[8 * t + (ldc - 1)] = acc[t][1];
+                    } else {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int kr = k0r + 8 * t + fr, jr = jc0r + 2 * fk + e;
-                    const i64 k = j0 + kr, j = j0 + jr;
-                    if (j < mcols && k >= 0 && k < n && kr - jr <= Cl && jr - kr <= Cu) c[(Cu + kr - jr) + j * ldc] = acc[t][e];
+                        for (int e = 0; e < 2; ++e) {
+                            const int dd = k0r + 8 * t + fr - (jc0r + 2 * fk + e);
+                            if (dd <= Cl && -dd <= Cu) cp0[8 * t + e * (ldc - 1)] = acc[t][e];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < GM_NT; ++t) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int kr = k0r + 8 * t + fr, jr = jc0r + 2 * fk + e;
+                        const i64 k = j0 + kr, j = j0 + jr;
+                        if (j < mcols && k >= 0 && k < n && kr - jr <= Cl && jr - kr <= Cu) cp0[8 * t + e * (ldc - 1)] = acc[t][e];
+                    }
                 }
             }
         }
         __syncthreads();  // the staged columns are overwritten by the next tile
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gbmm_bb_ring: the same tile arithmetic as gbmm_bb_dmma, restructured around the two things that bounded it (ncu,
+// profiles/gbmm_c3_r1_ncu.md): every CTA tile re-staged NA = TJ+Bl+Bu+7 columns of A for TJ output columns (3.2x the
+// algorithmic A traffic at C3, 31 % of all issued instructions) and nothing overlapped the staging.  Here a CTA walks
+// CONSECUTIVE column tiles and keeps the staged A columns in a ring: per tile only the TJ new columns (and the next
+// tile's B columns, double-buffered) are fetched, with cp.async, while the tensor cores work on the current tile.
+// One persistent CTA per SM, 16 warps; per-element operation order unchanged => bit-identical results.
+// ------------------------------------------------------------------------------------------------
+#define GR_THREADS 512
+template <int GM_NT>
+__global__ void __launch_bounds__(GR_THREADS, 1)
+gbmm_bb_ring(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, int Cu, double alpha,
+             const double *__restrict__ a, i64 lda, const double *__restrict__ b, i64 ldb, double beta,
+             double *__restrict__ c, i64 ldc, int PA, int PB, int NA, int RS, int TJ, i64 ntiles, i64 tiles_per_cta)
+{
+    extern __shared__ double sm[];
+    double *As = sm;                             // RS ring slots x PA
+    double *Bs0 = sm + (size_t)RS * PA;          // TJ columns x PB, two buffers
+    double *Bs1 = Bs0 + (size_t)TJ * PB;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = GR_THREADS / 32;
+    const int WA = Al + Au + 1, WB = Bl + Bu + 1;
+    const i64 t_begin = blockIdx.x * tiles_per_cta;
+    const i64 t_end = (t_begin + tiles_per_cta < ntiles) ? t_begin + tiles_per_cta : ntiles;
+    if (t_begin >= t_end) return;
+    for (int t = tid; t < RS * PA + 2 * TJ * PB; t += GR_THREADS) sm[t] = 0.0;  // pads are never written again
+    __syncthreads();
+    const i64 vorg = 4 * floordiv(t_begin * TJ - Bu, 4);  // ring origin: column v lives in slot (v - vorg) mod RS
+    auto stageA = [&](i64 vfirst, int ncols) {
+        for (int s = wid; s < ncols; s += NW) {
+            const i64 v = vfirst + s;
+            double *dst = As + (size_t)((unsigned)(v - vorg) % (unsigned)RS) * PA + GM_PAD;
+            int rlo = 1, rhi = 0;  // band rows r with 0 <= v - Au + r < n
+            if (v >= 0 && v < nu) {
+                rlo = (v < Au) ? (int)(Au - v) : 0;
+                rhi = (int)imin64_d((i64)WA - 1, n - 1 - v + Au);
+            }
+            const double *src = a + (rlo <= rhi ? v * lda : 0);
+            if (rlo == 0 && rhi == WA - 1) {
+                for (int r = lane; r < WA; r += 32) cp_async8_zfill(dst + r, src + r, true);
+            } else {
+                for (int r = lane; r < WA; r += 32) {
+                    const bool ok = r >= rlo && r <= rhi;
+                    cp_async8_zfill(dst + r, ok ? src + r : a, ok);
+                }
+            }
+        }
+    };
+    auto stageB = [&](double *Bs, i64 j0) {
+        for (int s = wid; s < TJ; s += NW) {
+            const i64 j = j0 + s;
+            double *dst = Bs + (size_t)s * PB + GM_PAD;
+            int rlo = 1, rhi = 0;  // band rows r with 0 <= j - Bu + r < nu
+            if (j < mcols) {
+                rlo = (j < Bu) ? (int)(Bu - j) : 0;
+                rhi = (int)imin64_d((i64)WB - 1, nu - 1 - j + Bu);
+            }
+            const double *src = b + (rlo <= rhi ? j * ldb : 0);
+            if (rlo == 0 && rhi == WB - 1) {
+                for (int r = lane; r < WB; r += 32) cp_async8_zfill(dst + r, src + r, true);
+            } else {
+                for (int r = lane; r < WB; r += 32) {
+                    const bool ok = r >= rlo && r <= rhi;
+                    cp_async8_zfill(dst + r, ok ? src + r : b, ok);
+                }
+            }
+        }
+    };
+    stageA(vorg, NA);
+    stageB(Bs0, t_begin * TJ);
+    cp_async_wait_all();
+    __syncthreads();
+    const int fr = lane >> 2, fk = lane & 3;   // fragment coordinates: A (row fr, k fk), B (k fk, col fr)
+    const int ntile_rows = (Cu + Cl + 8 + 7 + 7) / 8;          // row tiles that can touch one 8-column block
+    const int nchunks = (ntile_rows + GM_NT - 1) / GM_NT;
+    const int items_per_ct = (TJ / 8) * nchunks;               // work items (8 columns x GM_NT row tiles) of one CTA tile
+    const unsigned span = (unsigned)(Al + Au + 10);
+    const int ringlen = RS * PA;
+    const int astep = 4 * (PA - 1);
+    const bool scale = alpha != 1.0;
+    // Items differ in length (the V range shrinks towards the band edges), so warps draw them from a ticket counter
+    // instead of a fixed round-robin: the per-tile barrier then waits for at most one item.
+    __shared__ unsigned ticket_ctr;
+    if (tid == 0) ticket_ctr = NW;  // tickets 0..NW-1 are handed out statically
+    unsigned ticket = wid;          // next item of this warp, numbered across all CTA tiles of this CTA
+    __syncthreads();
+    for (i64 tile = t_begin; tile < t_end; ++tile) {
+        const i64 j0 = tile * TJ;
+        const i64 vbase = vorg + (tile - t_begin) * TJ;  // = 4*floor((j0-Bu)/4): TJ is a multiple of 4
+        const int seq = (int)(tile - t_begin);
+        const double *Bs = (seq & 1) ? Bs1 : Bs0;
+        if (tile + 1 < t_end) {  // next tile's new A columns and its B columns, in flight during this tile's DMMAs
+            stageA(vbase + NA, TJ);
+            stageB((seq & 1) ? Bs0 : Bs1, j0 + TJ);
+        }
+        const int kfirst_r = (int)(8 * floordiv(j0 - Cu, 8) - j0);
+        const int vbase_r = (int)(vbase - j0);
+        const int slot_base = (int)((unsigned)(vbase - vorg) % (unsigned)RS);
+        const unsigned tk0 = (unsigned)seq * (unsigned)items_per_ct, tk1 = tk0 + (unsigned)items_per_ct;
+        while (ticket < tk1) {
+            const int item = (int)(ticket - tk0);
+            const int jb = item / nchunks, ch = item - jb * nchunks;
+            const int jc0r = 8 * jb;
+            if (j0 + jc0r < mcols) {
+                const int k0r = kfirst_r + 8 * jb + 8 * GM_NT * ch;
+                double acc[GM_NT][2];
+                const bool inner = j0 + jc0r + 7 < mcols && j0 + k0r >= 0 && j0 + k0r + 8 * GM_NT - 1 < n;
+                double *cp0 = c + (Cu + (k0r + fr) - (jc0r + 2 * fk)) + (j0 + jc0r + 2 * fk) * ldc;
+                if (beta == 0.0) {
+#pragma unroll
+                    for (int t = 0; t < GM_NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < GM_NT; ++t) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int kr = k0r + 8 * t + fr, jr = jc0r + 2 * fk + e;
+                            const i64 k = j0 + kr, j = j0 + jr;
+                            const bool in = j < mcols && k >= 0 && k < n && kr - jr <= Cl && jr - kr <= Cu;
+                            acc[t][e] = in ? __dmul_rn(beta, cp0[8 * t + e * (ldc - 1)]) : 0.0;
+                        }
+                    }
+                }
+                int v0 = max(jc0r - Bu, k0r - Al), v1 = min(jc0r + 7 + Bl, k0r + 8 * GM_NT - 1 + Au);
+                if ((i64)v0 < -j0) v0 = (int)(-j0);
+                if ((i64)v1 > nu - 1 - j0) v1 = (int)(nu - 1 - j0);
+                v0 = (int)(4 * floordiv(j0 + v0, 4) - j0);
+                // B(v, j) -> Bs[jr*PB + PAD + v - jr + Bu];  A(k, v) -> As[slot(v)*PA + PAD + k - v + Au]
+                const double *bp = Bs + (size_t)(jc0r + fr) * PB + GM_PAD + Bu - (jc0r + fr) + fk + v0;
+                int aslot = slot_base + (v0 - vbase_r);  // ring slot of column v0: a multiple of 4, the ring wraps between steps
+                if (aslot >= RS) aslot -= RS;
+                const double *ap = As + (size_t)(aslot + fk) * PA + GM_PAD + Au - (v0 + fk) + k0r + fr;
+                int d0 = k0r - v0 + Au + 7;   // tile t meets the band of A columns [v, v+3] iff 0 <= d0 + 8t <= span
+                const int nsteps = (v1 >= v0) ? (v1 - v0) / 4 + 1 : 0;
+                int n1 = (RS - aslot) / 4;    // steps before the ring wraps
+                if (n1 > nsteps) n1 = nsteps;
+                for (int part = 0; part < 2; ++part) {
+                    const int ns = part ? nsteps - n1 : n1;
+                    if (part) ap -= ringlen;
+                    for (int st = 0; st < ns; ++st) {
+                        double bf = *bp;
+                        if (scale) bf = __dmul_rn(alpha, bf);
+#pragma unroll
+                        for (int t = 0; t < GM_NT; ++t) {
+                            if ((unsigned)(d0 + 8 * t) <= span) {  // warp-uniform
+                                const double af = ap[8 * t];
+                                dmma884(acc[t][0], acc[t][1], af, bf);
+                            }
+                        }
+                        bp += 4;
+                        ap += astep;
+                        d0 -= 4;
+                    }
+                }
+                if (inner) {
+#pragma unroll
+                    for (int t = 0; t < GM_NT; ++t) {
+                        const int dlo = k0r + 8 * t - jc0r - 7, dhi = dlo + 14;
+                        if (dhi <= Cl && dlo >= -Cu) {
+                            cp0[8 * t] = acc[t][0];
+                            cp0[8 * t + (ldc - 1)] = acc[t][1];
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int dd = k0r + 8 * t + fr - (jc0r + 2 * fk + e);
+                                if (dd <= Cl && -dd <= Cu) cp0[8 * t + e * (ldc - 1)] = acc[t][e];
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < GM_NT; ++t) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int kr = k0r + 8 * t + fr, jr = jc0r + 2 * fk + e;
+                            const i64 k = j0 + kr, j = j0 + jr;
+                            if (j < mcols && k >= 0 && k < n && kr - jr <= Cl && jr - kr <= Cu) cp0[8 * t + e * (ldc - 1)] = acc[t][e];
+                        }
+                    }
+                }
+            }
+            unsigned nt = 0;
+            if (lane == 0) nt = atomicAdd(&ticket_ctr, 1u);
+            ticket = __shfl_sync(0xffffffffu, nt, 0);
+        }
+        cp_async_wait_all();
+        __syncthreads();  // next tile's columns have landed; this tile's oldest TJ ring slots may be overwritten
     }
 }
 
@@ -230,15 +455,56 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
     const i64 WA = Al + Au + 1, WB = Bl + Bu + 1;
     if (alpha != 0.0 && mprod > 0 && WA >= 9 && WB >= 9 && Cl == imin64(n - 1, Al + Bl) && Cu == imin64(m - 1, Au + Bu)) {
         const int PA = pitch5((int)WA + 2 * GM_PAD), PB = pitch5((int)WB + 2 * GM_PAD);
+        // Two tensor-core kernels: the two-CTA-per-SM tile kernel while a tile's staged columns fit in half an SM's shared
+        // memory (C3: 4.45 ms), else the persistent ring kernel (one CTA per SM; C3: 4.63 ms, (64,64)x(64,64): 12.4 ms
+        // where the sweep kernel took 110 ms).  BMB200_GBMM_RING=1 forces the ring kernel, =0 disables it.
+        static const int ring_env = getenv("BMB200_GBMM_RING") ? atoi(getenv("BMB200_GBMM_RING")) : -1;
+        const bool tile_fits = ((size_t)(GM_TJ + Bl + Bu + 7) * PA + (size_t)GM_TJ * PB) * sizeof(double) <= 110 * 1024;
+        const bool try_ring = ring_env == 1 || (ring_env != 0 && !tile_fits);
+        for (int TJ = 32; TJ >= 8 && try_ring && jsplit == 0; TJ >>= 1) {  // ring kernel: widest tile whose ring fits
+            const int NAr = (int)(TJ + Bl + Bu + 4 + 3);
+            const int RS = 4 * ((NAr + TJ + 3) / 4);
+            const size_t smem_r = ((size_t)RS * PA + 2 * (size_t)TJ * PB) * sizeof(double);
+            if (smem_r > 225 * 1024) continue;
+            const i64 ntiles = cdiv64(mprod, TJ);
+            const i64 blocks = imin64(ntiles, (i64)h->sm_count);
+            const i64 tpc = cdiv64(ntiles, blocks);
+            if (tpc * TJ + Bl + Bu + 64 >= ((i64)1 << 31)) break;
+            static const int rnt = getenv("BMB200_GBMM_NT") ? atoi(getenv("BMB200_GBMM_NT")) : 3;  // tuning switch
+#define GR_LAUNCH(NT)                                                                                                                  \
+    do {                                                                                                                               \
+        BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_ring<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));                 \
+        gbmm_bb_ring<NT><<<(unsigned)cdiv64(ntiles, tpc), GR_THREADS, smem_r, h->stream>>>(n, nu, mprod, (int)Al, (int)Au, (int)Bl,    \
+                                                                                           (int)Bu, (int)Cl, (int)Cu, alpha, dA, lda, \
+                                                                                           dB, ldb, beta, dC, ldc, PA, PB, NAr, RS,   \
+                                                                                           TJ, ntiles, tpc);                          \
+    } while (0)
+            if (rnt == 2) GR_LAUNCH(2); else if (rnt == 4) GR_LAUNCH(4); else if (rnt == 6) GR_LAUNCH(6); else GR_LAUNCH(3);
+#undef GR_LAUNCH
+            BMB_LAUNCH_CHECK(h);
+            jsplit = mprod;
+        }
         const int NA = (int)(GM_TJ + Bl + Bu + 4 + 3);
         const size_t smem = ((size_t)NA * PA + (size_t)GM_TJ * PB) * sizeof(double);
-        if (smem <= 110 * 1024) {
-            BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (jsplit == 0 && smem <= 110 * 1024) {
             const i64 ntiles = cdiv64(mprod, GM_TJ);
             const i64 blocks = imin64(ntiles, (i64)h->sm_count * 2);
-            gbmm_bb_dmma<<<(unsigned)blocks, GM_THREADS, smem, h->stream>>>(n, nu, mprod, (int)Al, (int)Au, (int)Bl, (int)Bu,
-                                                                         (int)Cl, (int)Cu, alpha, dA, lda, dB, ldb, beta,
-                                                                         dC, ldc, PA, PB, NA, ntiles);
+            static const int nt_env = getenv("BMB200_GBMM_NT") ? atoi(getenv("BMB200_GBMM_NT")) : 3;  // tuning switch
+#define GM_LAUNCH(NT)                                                                                                          \
+    do {                                                                                                                       \
+        BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_dmma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        gbmm_bb_dmma<NT><<<(unsigned)blocks, GM_THREADS, smem, h->stream>>>(n, nu, mprod, (int)Al, (int)Au, (int)Bl, (int)Bu,  \
+                                                                            (int)Cl, (int)Cu, alpha, dA, lda, dB, ldb, beta,  \
+                                                                            dC, ldc, PA, PB, NA, ntiles);                     \
+    } while (0)
+            switch (nt_env) {
+            case 2: GM_LAUNCH(2); break;
+            case 4: GM_LAUNCH(4); break;
+            case 6: GM_LAUNCH(6); break;
+            case 9: GM_LAUNCH(9); break;
+            default: GM_LAUNCH(3); break;
+            }
+#undef GM_LAUNCH
             BMB_LAUNCH_CHECK(h);
             jsplit = mprod;
         }

@@ -76,6 +76,23 @@ def test_gbmm_tensor_core_path_multi_tile(bm, oracle_c, rng, shape):
     assert np.array_equal(Band(Cm.banddata_host(), n, Cl, Cu).dense(), Band(ref, n, Cl, Cu).dense())
 
 
+@pytest.mark.parametrize("shape", [(3000, 3000, 3000, 64, 64, 64, 64), (2500, 2500, 2500, 48, 48, 48, 48), (2100, 2000, 2300, 100, 40, 50, 90),
+                                   (5000, 5000, 5000, 40, 60, 70, 30)])
+def test_gbmm_ring_kernel_wide_bands(bm, oracle_c, rng, shape):
+    """Bands too wide for the two-CTA tile kernel: the persistent ring kernel (gbmm_bb_ring: staged A columns kept in a
+    shared-memory ring across consecutive column tiles, 8/16/32-column tiles by fit).  Same per-element order => same bits."""
+    n, nu, m, Al, Au, Bl, Bu = shape
+    A, B = brand(rng, n, nu, Al, Au, corners=np.nan), brand(rng, nu, m, Bl, Bu, corners=np.nan)
+    Cl, Cu = min(n - 1, Al + Bl), min(m - 1, Au + Bu)
+    for alpha, beta in [(1.0, 0.0), (-0.75, 1.25)]:
+        C0 = brand(rng, n, m, Cl, Cu)
+        ref = C0.data.copy(order="F")
+        gbmm_kernel(oracle_c, alpha, A.data, B.data, beta, ref, n, nu, m, Al, Au, Bl, Bu, Cl, Cu)
+        Cm = up(bm, C0)
+        bm.mul_(Cm, up(bm, A), up(bm, B), alpha, beta)
+        assert np.array_equal(Band(Cm.banddata_host(), n, Cl, Cu).dense(), Band(ref, n, Cl, Cu).dense())
+
+
 def test_gbmm_wider_C_and_banderror(bm, rng):
     """C with extra bands gets zeros/β-scaling there (test_broadcasting.jl:457-478); too few bands ⇒ BandError
     unless the missing bands are structurally zero (test_linalg.jl:272-295)."""
