@@ -61,6 +61,69 @@ def run_c5(bm, N=1024):
             "pivots_identity": ident, "max_residual_over_max_x": res}
 
 
+def cpu_extras(L, cores):
+    """The reference's CPU path for C1/C3/C4/C5 beside the GPU numbers: OpenBLAS 0.3.30 entered through the
+    Fortran symbols the reference ccalls, replaying its call sequences from C (oracle/blasdriver.c) on BOUNDED samples of
+    each workload; every entry states its sample and the linear extrapolation to the full size."""
+    import ctypes as C
+
+    i64, dbl, vp = C.c_int64, C.c_double, C.c_void_p
+    L.drv_gbmv.restype = dbl
+    L.drv_gbmv.argtypes = [i64] * 4 + [dbl, vp, i64, vp, dbl, vp]
+    L.drv_gbmm.restype = dbl
+    L.drv_gbmm.argtypes = [i64] * 9 + [dbl, vp, i64, vp, i64, dbl, vp, i64]
+    L.drv_gbtrf.restype = dbl
+    L.drv_gbtrf.argtypes = [i64] * 4 + [vp, i64, vp, vp]
+    L.drv_gbtrs.restype = dbl
+    L.drv_gbtrs.argtypes = [i64] * 4 + [vp, i64, vp, vp, i64, vp]
+    rng = np.random.default_rng(7)
+    out = {"cores": cores, "library": "OpenBLAS 0.3.30 ILP64 (numpy's), dgbmv pinned to 1 thread, LAPACK calls on all cores"}
+
+    def lu_solve(n, l, u, nrhs, dominant=False):
+        ldab = 2 * l + u + 1
+        ab = np.zeros((ldab, n), order="F")
+        ab[l:, :] = rng.random((l + u + 1, n))
+        if dominant:
+            ab[l + u, :] += 2.0 * (l + u + 1)
+        ipiv = np.zeros(n, dtype=np.int64)
+        info = np.zeros(1, dtype=np.int64)
+        L.drv_set_threads(cores)
+        tf = L.drv_gbtrf(n, n, l, u, ab.ctypes.data, ldab, ipiv.ctypes.data, info.ctypes.data)
+        b = np.asfortranarray(rng.random((n, nrhs)))
+        ts = L.drv_gbtrs(n, l, u, nrhs, ab.ctypes.data, ldab, ipiv.ctypes.data, b.ctypes.data, n, info.ctypes.data)
+        return 1e3 * tf, 1e3 * ts
+
+    # C1: the README workload in full
+    n = 10000
+    a = np.asfortranarray(rng.random((8, n)))
+    x, y = rng.standard_normal(n), np.zeros(n)
+    L.drv_set_threads(1)
+    t_ab = min(L.drv_gbmv(n, n, 4, 3, 1.0, a.ctypes.data, 8, x.ctypes.data, 0.0, y.ctypes.data) for _ in range(5))
+    c = np.zeros((15, n), order="F")
+    t_aa = min(L.drv_gbmm(n, n, n, 4, 3, 4, 3, 8, 6, 1.0, a.ctypes.data, 8, a.ctypes.data, 8, 0.0, c.ctypes.data, 15) for _ in range(3))
+    tf, ts = lu_solve(n, 4, 3, 1)
+    out["C1"] = {"Ab_us": round(1e6 * t_ab, 1), "AA_us": round(1e6 * t_aa, 1), "solve_us": round(1e3 * (tf + ts), 1), "sample": "full size"}
+    # C3: _gbmm! = one dgbmv_ per column of C (gbmm.jl:306-339); sample of 2^18 columns, linear in n
+    ns, full = 1 << 18, 1 << 22
+    a = np.asfortranarray(rng.random((65, ns)))
+    b = np.asfortranarray(rng.random((65, ns)))
+    c = np.zeros((129, ns), order="F")
+    L.drv_set_threads(1)
+    t = L.drv_gbmm(ns, ns, ns, 32, 32, 32, 32, 64, 64, 1.0, a.ctypes.data, 65, b.ctypes.data, 65, 0.0, c.ctypes.data, 129)
+    out["C3"] = {"sample": "n=2^18 of 2^22 columns", "sample_ms": round(1e3 * t, 1), "full_ms_extrapolated": round(1e3 * t * full / ns, 1)}
+    del a, b, c
+    # C4: dgbtrf on the full matrix; dgbtrs on 16 of the 256 right-hand sides, linear in nrhs
+    tf, ts = lu_solve(1 << 20, 16, 16, 16)
+    out["C4"] = {"sample": "n=2^20 in full; 16 of 256 RHS for dgbtrs", "gbtrf_ms": round(tf, 1), "gbtrs_sample_ms": round(ts, 1),
+                 "gbtrs_full_ms_extrapolated": round(ts * 256 / 16, 1)}
+    # C5: n=2^20, l=u=1024 needs 26 GB of host memory and ~30 s; sample n=2^14, linear in n (work per column is constant)
+    ns, full = 1 << 14, 1 << 20
+    tf, ts = lu_solve(ns, 1024, 1024, 1, dominant=True)
+    out["C5"] = {"sample": "n=2^14 of 2^20 columns, l=u=1024, diagonally dominant, 1 RHS", "lu_sample_ms": round(tf, 1), "solve_sample_ms": round(ts, 1),
+                 "lu_full_ms_extrapolated": round(tf * full / ns, 1), "solve_full_ms_extrapolated": round(ts * full / ns, 1)}
+    return out
+
+
 def run_extras(bm, c3_n=1 << 22, c4_n=1 << 20, c4_rhs=256):
     out = {}
     # ---- C1 ----

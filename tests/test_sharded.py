@@ -52,3 +52,13 @@ def test_sharded_gbmv_nccl_world2():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     _run("nccl", 2)
+
+
+@pytest.mark.gpu
+def test_sharded_gbmv_nccl_world4():
+    """Four ranks: interior ranks have two DIFFERENT neighbours (at world size 2 both mailboxes belong to the same peer)."""
+    import torch
+
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs >= 4 GPUs (gpurun --gpus 4)")
+    _run("nccl", 4)
