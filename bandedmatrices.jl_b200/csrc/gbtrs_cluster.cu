@@ -209,13 +209,14 @@ struct GcLocal {
 // One sweep.  Step t handles row block blk(t) (forward: t, backward: PB-1-t); the triangle of step t needs the updates
 // of steps t-KB .. t-1 applied to its rows in that order: far steps [t-KB, t-DN-1] by a worker, near steps by the leader.
 // Shared memory of every CTA: hand[GC_HS][16] cells (used in the leader), then xs[xslots][16] cells.
-template <bool FWD>
-__device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *smem, int xslots, i64 n, int kl, int ku,
+// `kv` = row of the diagonal inside a column of `ab`, `bw` = reach of the sweep below (FWD) / above (!FWD) the diagonal,
+// DIV = divide by the diagonal (non-unit triangle): gbtrs is <FWD,no DIV>(kv=kl+ku, bw=kl) then <!FWD,DIV>(kv, bw=kv);
+// tbsv 'U' is <!FWD, DIV = non-unit>(kv=k, bw=k); tbsv 'L' is <FWD, DIV = non-unit>(kv=0, bw=k).
+template <bool FWD, bool DIV>
+__device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *smem, int xslots, i64 n, int kv, int bw,
                                          const double *__restrict__ ab, i64 ldab, double *x, int *gabort, int pfdist, long long *stats, GcLocal &loc)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, i = lane & 15;
-    const int kv = kl + ku;
-    const int bw = FWD ? kl : kv;                   // reach of the sweep below / above the diagonal
     const i64 PB = (n + GC_NB - 1) / GC_NB;
     const int KB = (bw + GC_NB - 1) / GC_NB;        // largest block distance with an in-band entry
     const int DN = KB < GC_D ? KB : GC_D;
@@ -250,7 +251,7 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
                 // operands of the diagonal triangle (independent of the right-hand side: loaded before any wait)
                 double T[GC_NB];
                 unsigned tm = 0;
-                const bool tint = rowok && (b + 1) * GC_NB <= n && (FWD ? kl : kv) >= GC_NB - 1;  // whole 16 x 16 block in band and matrix
+                const bool tint = rowok && (b + 1) * GC_NB <= n && bw >= GC_NB - 1;  // whole 16 x 16 block in band and matrix
                 if (tint) {  // unmasked loads (the other triangle's entries are in bounds and discarded below)
                     const double *pt = ab + (kv + i) + (b * GC_NB) * ldab;
 #pragma unroll
@@ -260,14 +261,14 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
 #pragma unroll
                     for (int c = 0; c < GC_NB; ++c) {
                         const i64 col = b * GC_NB + c;
-                        const bool ok = FWD ? (rowok && c < i && i - c <= kl) : (c > i && col < n && c - i <= kv);
+                        const bool ok = FWD ? (rowok && c < i && i - c <= bw) : (c > i && col < n && c - i <= bw);
                         T[c] = ok ? __ldg(ab + (kv + i - c) + col * ldab) : 0.0;
                         tm |= (unsigned)ok << c;
                     }
                 }
                 double Ud = 1.0, rcp = 1.0;
                 bool dsafe = false;
-                if (!FWD) {
+                if (DIV) {
                     Ud = rowok ? __ldg(ab + kv + r * ldab) : 1.0;
                     rcp = 1.0 / Ud;  // one IEEE reciprocal per row, off the chain (gb_div: two Markstein corrections)
                     dsafe = gb_div_safe_divisor(Ud);
@@ -310,18 +311,20 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
                     for (int c = 0; c < GC_NB; ++c) T[c] = ((tm >> c) & 1u) ? T[c] : 0.0;
                 }
                 double fin = xi;
-                if (FWD) {
-                    if (kl >= GC_NB - 1) {
+                if (!DIV) {
+                    if (bw >= GC_NB - 1) {
 #pragma unroll
-                        for (int c = 0; c < GC_NB - 1; ++c) {
+                        for (int cc = 0; cc < GC_NB - 1; ++cc) {  // the last column has no row left to update
+                            const int c = FWD ? cc : GC_NB - 1 - cc;
                             const double u = __shfl_sync(0xffffffffu, xi, c);
                             fin = (i == c) ? xi : fin;
                             xi = fma(-u, T[c], xi);
                         }
-                        xi = (i == GC_NB - 1) ? xi : fin;
+                        xi = (i == (FWD ? GC_NB - 1 : 0)) ? xi : fin;
                     } else {
 #pragma unroll
-                        for (int c = 0; c < GC_NB - 1; ++c) {
+                        for (int cc = 0; cc < GC_NB; ++cc) {
+                            const int c = FWD ? cc : GC_NB - 1 - cc;
                             const double u = __shfl_sync(0xffffffffu, xi, c);
                             xi = gc_fma_if((tm >> c) & 1u, -u, T[c], xi);
                         }
@@ -332,9 +335,10 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
                     // row and lane c's is the one broadcast, so the warp stays converged and no call sits inside the chain.
                     const double xsave = xi;
                     bool slow = false;
-                    if (kv >= GC_NB - 1) {
+                    if (bw >= GC_NB - 1) {
 #pragma unroll
-                        for (int c = GC_NB - 1; c >= 0; --c) {
+                        for (int cc = 0; cc < GC_NB; ++cc) {
+                            const int c = FWD ? cc : GC_NB - 1 - cc;
                             const double q0 = __dmul_rn(xi, rcp);
                             const double q1 = fma(fma(-q0, Ud, xi), rcp, q0);
                             const double q2 = fma(fma(-q1, Ud, xi), rcp, q1);
@@ -347,7 +351,8 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
                         xi = fin;
                     } else {
 #pragma unroll
-                        for (int c = GC_NB - 1; c >= 0; --c) {
+                        for (int cc = 0; cc < GC_NB; ++cc) {
+                            const int c = FWD ? cc : GC_NB - 1 - cc;
                             const double q0 = __dmul_rn(xi, rcp);
                             const double q1 = fma(fma(-q0, Ud, xi), rcp, q0);
                             const double q2 = fma(fma(-q1, Ud, xi), rcp, q1);
@@ -360,7 +365,8 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
                     }
                     if (__any_sync(0xffffffffu, slow)) {  // an operand outside the safe range: redo with IEEE divisions
                         xi = xsave;
-                        for (int c = GC_NB - 1; c >= 0; --c) {
+                        for (int cc = 0; cc < GC_NB; ++cc) {
+                            const int c = FWD ? cc : GC_NB - 1 - cc;
                             if (i == c && rowok) xi = gb_div_ieee(xi, Ud);
                             const double q = __shfl_sync(0xffffffffu, xi, c);
                             if ((tm >> c) & 1u) xi = fma(-q, T[c], xi);
@@ -400,10 +406,10 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
                 const i64 col = bs * GC_NB + lane;
                 if (lane < GC_NB && col < n) {
                     if (FWD) {
-                        const i64 lm = (n - 1 - col < kl) ? n - 1 - col : kl;
+                        const i64 lm = (n - 1 - col < bw) ? n - 1 - col : bw;
                         gc_prefetch_l2_range(ab + col * ldab + (kv + 1), (int)lm);
                     } else {
-                        gc_prefetch_l2_range(ab + col * ldab, kv + 1);
+                        gc_prefetch_l2_range(ab + col * ldab + (kv - bw), bw + 1);
                     }
                 }
             }
@@ -449,6 +455,10 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
     }
 }
 
+// MODE 0: gbtrs (unit forward sweep with the multipliers below row kl+ku, then dividing backward sweep over kl+ku rows);
+// MODE 1: backward sweep only, unit diagonal (tbsv 'U','N','U'); MODE 2 / 3: forward sweep only, unit / non-unit
+// diagonal in row 0 of the band array (tbsv 'L').  tbsv 'U','N','N' is MODE 0 with kl = 0.
+template <int MODE>
 __global__ void __launch_bounds__(GC_THREADS, 1)
 gbtrs_cluster_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab, double *__restrict__ bmat, i64 ldb, int xslots,
                      int *gabort, int pfdist, long long *stats)
@@ -462,15 +472,23 @@ gbtrs_cluster_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 l
     for (int k = threadIdx.x; k < (GC_HS + xslots) * GC_NB; k += blockDim.x) gc_smem[k] = GcCell{0u, 0u, 0u, 0u};
     if (threadIdx.x < GC_HS) loc.ltag[threadIdx.x] = 0u;
     cluster.sync();
-    if (kl > 0) gc_sweep<true>(cluster, gc_smem, xslots, n, kl, ku, ab, ldab, x, gabort, pfdist, stats, loc);
-    cluster.sync();  // forward results are in global memory; every ring is quiescent
-    gc_sweep<false>(cluster, gc_smem, xslots, n, kl, ku, ab, ldab, x, gabort, pfdist, stats, loc);
+    if (MODE == 0) {
+        if (kl > 0) gc_sweep<true, false>(cluster, gc_smem, xslots, n, kl + ku, kl, ab, ldab, x, gabort, pfdist, stats, loc);
+        cluster.sync();  // forward results are in global memory; every ring is quiescent
+        gc_sweep<false, true>(cluster, gc_smem, xslots, n, kl + ku, kl + ku, ab, ldab, x, gabort, pfdist, stats, loc);
+    } else if (MODE == 1) {
+        gc_sweep<false, false>(cluster, gc_smem, xslots, n, ku, ku, ab, ldab, x, gabort, pfdist, stats, loc);
+    } else if (MODE == 2) {
+        gc_sweep<true, false>(cluster, gc_smem, xslots, n, 0, kl, ab, ldab, x, gabort, pfdist, stats, loc);
+    } else {
+        gc_sweep<true, true>(cluster, gc_smem, xslots, n, 0, kl, ab, ldab, x, gabort, pfdist, stats, loc);
+    }
     cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
 // returns 1 when not applicable (the caller then runs the single-CTA kernel), 0 on success, <0 on error.
-// The caller has verified ipiv = 1:n.
-int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb)
+// mode 0: the caller has verified ipiv = 1:n.  modes 1-3: triangular band solves (see the kernel).
+int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb)
 {
     static const bool off = getenv("BMB200_GBTRS_NOCLUSTER") != nullptr;
     static const int csize_env = getenv("BMB200_GBTRS_CLUSTER") ? atoi(getenv("BMB200_GBTRS_CLUSTER")) : 0;
@@ -483,8 +501,12 @@ int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doub
     while (xslots < KBmax + GC_D + 4) xslots <<= 1;
     const size_t smem = (size_t)(GC_HS + xslots) * GC_NB * sizeof(GcCell);
     if (smem > 200 * 1024) return 1;
-    BMB_CUDA(h, cudaFuncSetAttribute(gbtrs_cluster_noswap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BMB_CUDA(h, cudaFuncSetAttribute(gbtrs_cluster_noswap, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    typedef void (*kern_t)(i64, int, int, const double *, i64, double *, i64, int, int *, int, long long *);
+    static const kern_t kerns[4] = {gbtrs_cluster_noswap<0>, gbtrs_cluster_noswap<1>, gbtrs_cluster_noswap<2>, gbtrs_cluster_noswap<3>};
+    if (mode < 0 || mode > 3) return 1;
+    const kern_t kern = kerns[mode];
+    BMB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BMB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     int *gabort = h->d_info + 17;
     BMB_CUDA(h, cudaMemsetAsync(gabort, 0, sizeof(int), h->stream));
     // cluster size 8 (portable; 15 clusters co-resident): measured equal to 16 at l=u=1024 -- the leader chain is the bound
@@ -504,7 +526,7 @@ int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doub
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         int nclusters = 0;
-        const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, gbtrs_cluster_noswap, &cfg);
+        const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
         static const bool dbg = getenv("BMB200_DEBUG") != nullptr;
         if (dbg) fprintf(stderr, "[bmb200] gbtrs_cluster: cluster size %d -> %s, %d co-resident clusters, smem %zu\n", csize, cudaGetErrorString(e), nclusters, smem);
         if (e == cudaSuccess && nclusters > 0) break;
@@ -517,7 +539,7 @@ int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doub
         dstats = (long long *)h->scratch;
         BMB_CUDA(h, cudaMemsetAsync(dstats, 0, 24 * sizeof(long long), h->stream));
     }
-    BMB_CUDA(h, cudaLaunchKernelEx(&cfg, gbtrs_cluster_noswap, n, (int)kl, (int)ku, dAB, ldab, dB, ldb, xslots, gabort, pfdist, dstats));
+    BMB_CUDA(h, cudaLaunchKernelEx(&cfg, kern, n, (int)kl, (int)ku, dAB, ldab, dB, ldb, xslots, gabort, pfdist, dstats));
     h->launches++;
     if (want_stats) {
         long long hs[24];
@@ -539,4 +561,9 @@ int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doub
         return BMB200_ERR_CUDA;
     }
     return 0;
+}
+
+int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb)
+{
+    return bmb_cluster_solve(h, 0, n, kl, ku, nrhs, dAB, ldab, dB, ldb);
 }

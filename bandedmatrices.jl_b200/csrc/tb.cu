@@ -1,0 +1,87 @@
+// tb.cu -- triangular band solve / multiply on the device: tbsv! and tbmv! of the reference (src/blas.jl:71-141), reached
+// from ldiv!/lmul! of UpperTriangular / LowerTriangular{<:BandedMatrix} (src/tribanded.jl:47-84).  SURVEY.md 8(f) rank 2:
+// the same sweeps as the back substitution inside gbtrs, exposed on BLAS triangular-band storage
+//   'U': T[i,j] at a[(k + i - j) + j*lda]      'L': T[i,j] at a[(i - j) + j*lda]        (0-based, i - j within the band)
+// trans = 'N' only (the reference uses 'T' for row-major layouts only; not built here).  incx must be 1.
+//   * bmb200_dtbsv: the cluster pipeline of gbtrs_cluster.cu, one sweep (OpenBLAS tbsv_{U,L}: true division by the
+//     diagonal unless unit, then fma(-x_j, T[i,j], x_i)) => bit-identical to the reference CPU path.
+//   * bmb200_dtbmv: one thread per row, d_i*x_i (x_i if unit) then fma(x_j, T[i,j], .) over j ascending ('U') or
+//     descending ('L') -- the per-row order of OpenBLAS' column sweep -- into a scratch vector, then copied back.
+#include "common.cuh"
+
+int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
+
+__global__ void __launch_bounds__(256)
+tbmv_rows(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda, const double *__restrict__ x, double *__restrict__ y)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        double acc = x[i];
+        if (up) {
+            if (!unit) acc = __dmul_rn(acc, a[k + i * lda]);
+            const i64 j1 = (i + k < n - 1) ? i + k : n - 1;
+            const double *p = a + (k - 1) + (i + 1) * lda;  // T[i, i+1]; next column: + lda - 1
+            for (i64 j = i + 1; j <= j1; ++j, p += lda - 1) acc = fma(x[j], *p, acc);
+        } else {
+            if (!unit) acc = __dmul_rn(acc, a[i * lda]);
+            const i64 j0 = (i - k > 0) ? i - k : 0;
+            const double *p = a + 1 + (i - 1) * lda;        // T[i, i-1]; previous column: - lda + 1
+            for (i64 j = i - 1; j >= j0; --j, p -= lda - 1) acc = fma(x[j], *p, acc);
+        }
+        y[i] = acc;
+    }
+}
+
+static int tb_check(char uplo, char trans, char diag, int64_t n, int64_t k, int64_t lda, int64_t incx, int &up, int &unit)
+{
+    up = (uplo == 'U' || uplo == 'u');
+    unit = (diag == 'U' || diag == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -2;
+    if (!(trans == 'N' || trans == 'n')) return -3;  // 'T' / 'C' (row-major layouts in the reference): not built
+    if (!unit && !(diag == 'N' || diag == 'n')) return -4;
+    if (n < 0) return -5;
+    if (k < 0) return -6;
+    if (lda < k + 1) return -8;
+    if (incx != 1) return -10;
+    return 0;
+}
+
+extern "C" int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const double *dA, int64_t lda,
+                            double *dx, int64_t incx)
+{
+    if (!h) return -1;
+    int up, unit;
+    const int rc0 = tb_check(uplo, trans, diag, n, k, lda, incx, up, unit);
+    if (rc0) return rc0;
+    if (n == 0) return 0;
+    if (!dA || !dx) return -7;
+    DeviceGuard g(h->device);
+    // 'U': diagonal in row k of the band array, reach k above it (mode 0 with kl = 0 divides, mode 1 does not);
+    // 'L': diagonal in row 0, reach k below it (mode 2 unit, mode 3 dividing)
+    const int mode = up ? (unit ? 1 : 0) : (unit ? 2 : 3);
+    const int rc = bmb_cluster_solve(h, mode, n, up ? 0 : k, up ? k : 0, 1, dA, lda, dx, n > 1 ? n : 1);
+    if (rc == 1) {
+        snprintf(h->err, sizeof(h->err), "dtbsv: band width %lld is not supported by the cluster pipeline on this device", (long long)k);
+        return BMB200_ERR_CUDA;
+    }
+    return rc;
+}
+
+extern "C" int bmb200_dtbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const double *dA, int64_t lda,
+                            double *dx, int64_t incx)
+{
+    if (!h) return -1;
+    int up, unit;
+    const int rc0 = tb_check(uplo, trans, diag, n, k, lda, incx, up, unit);
+    if (rc0) return rc0;
+    if (n == 0) return 0;
+    if (!dA || !dx) return -7;
+    if (k >= ((int64_t)1 << 30)) return -6;
+    DeviceGuard g(h->device);
+    if (bmb_ensure_scratch(h, (size_t)n * sizeof(double)) != 0) return BMB200_ERR_CUDA;
+    double *y = (double *)h->scratch;
+    const i64 blocks = imin64(cdiv64(n, 256), (i64)h->sm_count * 16);
+    tbmv_rows<<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, y);
+    BMB_LAUNCH_CHECK(h);
+    BMB_CUDA(h, cudaMemcpyAsync(dx, y, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}

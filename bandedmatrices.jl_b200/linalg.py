@@ -473,6 +473,65 @@ def ldiv_(F, B: torch.Tensor) -> torch.Tensor:
     return B
 
 
+# ---------------------------------------------------------------------------------------------------
+# Triangular band solve / multiply: tbsv! / tbmv! (src/blas.jl:71-141) and the UpperTriangular / LowerTriangular
+# {<:BandedMatrix} ldiv! / lmul! that reach them (src/tribanded.jl:47-84)
+# ---------------------------------------------------------------------------------------------------
+def _tb(fn_name: str, uplo: str, trans: str, diag: str, m: int, k: int, Adata: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """``Adata`` is the band array as this package stores it: shape (n, rows >= k+1), one column of the band per row of the
+    tensor, ``Adata.stride(0)`` = lda (so a row-range view of ``BandedMatrix.data`` passes straight through)."""
+    n = Adata.shape[0]
+    if Adata.shape[1] < k + 1:  # blas.jl:88,126
+        raise ValueError("triangular banded data missing")
+    if n != m:
+        raise DimensionMismatch(f"matrix is not square: dimensions are {n}, {m}")
+    if n != x.shape[0]:
+        raise DimensionMismatch(f"size of A is {n} != length(x) = {x.shape[0]}")
+    if x.dim() != 1 or _inc(x) != 1:
+        raise TypeError("x must be a contiguous vector")
+    if Adata.shape[1] > 1 and Adata.stride(1) != 1:  # chkstride1
+        raise ValueError("band rows of one column must be contiguous")
+    if n == 0:
+        return x
+    hd = _h(x)
+    lda = max(1, Adata.stride(0)) if n > 1 else max(1, Adata.shape[1])
+    rc = getattr(hd.lib, fn_name)(hd.h, uplo.encode(), trans.encode(), diag.encode(), n, k, vp(Adata.data_ptr()), lda,
+                                  vp(x.data_ptr()), 1)
+    hd.check(rc, fn_name[7:])
+    return x
+
+
+def tbsv_(uplo, trans, diag, m, k, Adata, x):
+    """``tbsv!(uplo, trans, diag, m, k, A, x)`` (src/blas.jl:121-141): x <- inv(T) x in place."""
+    return _tb("bmb200_dtbsv", uplo, trans, diag, m, k, Adata, x)
+
+
+def tbmv_(uplo, trans, diag, m, k, Adata, x):
+    """``tbmv!(uplo, trans, diag, m, k, A, x)`` (src/blas.jl:83-101): x <- T x in place."""
+    return _tb("bmb200_dtbmv", uplo, trans, diag, m, k, Adata, x)
+
+
+def _tri_data(uplo: str, A: BandedMatrix):
+    """bandeddata of the triangular view: rows 1:u+1 of A.data for 'U', rows u+1:u+l+1 for 'L'; bandwidth(A, bwdim)."""
+    if A.m != A.n:
+        raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")
+    if uplo == "U":
+        return A.data[:, : A.u + 1], A.u
+    return A.data[:, A.u:], A.l
+
+
+def ldiv_tri_(uplo: str, unit: bool, A: BandedMatrix, x: torch.Tensor) -> torch.Tensor:
+    """``ldiv!(UpperTriangular(A), x)`` / LowerTriangular / Unit* (src/tribanded.jl:75-84)."""
+    d, k = _tri_data(uplo, A)
+    return tbsv_(uplo, "N", "U" if unit else "N", A.m, k, d, x)
+
+
+def lmul_tri_(uplo: str, unit: bool, A: BandedMatrix, x: torch.Tensor) -> torch.Tensor:
+    """``lmul!(UpperTriangular(A), x)`` / LowerTriangular / Unit* (src/tribanded.jl:47-55)."""
+    d, k = _tri_data(uplo, A)
+    return tbmv_(uplo, "N", "U" if unit else "N", A.m, k, d, x)
+
+
 def factorize(A: BandedMatrix):
     """_factorize (linalg.jl:75): square -> lu; rectangular -> qr (out of scope here)."""
     if A.m != A.n:

@@ -79,7 +79,16 @@ class _CBackend:
         L.oracle_banded_mul.argtypes = [i64] * 9 + [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64]
         L.oracle_fill_lmul.restype = None
         L.oracle_fill_lmul.argtypes = [C.c_double, C.c_void_p, i64, i64, i64]
+        for f in (L.oracle_dtbsv, L.oracle_dtbmv):
+            f.restype = C.c_int
+            f.argtypes = [C.c_char, C.c_char, C.c_char, i64, i64, C.c_void_p, i64, C.c_void_p]
         self.L = L
+
+    def tbsv(self, uplo, trans, diag, n, k, a, lda, x):
+        return self.L.oracle_dtbsv(uplo.encode(), trans.encode(), diag.encode(), n, k, _ptr(a), lda, _ptr(x))
+
+    def tbmv(self, uplo, trans, diag, n, k, a, lda, x):
+        return self.L.oracle_dtbmv(uplo.encode(), trans.encode(), diag.encode(), n, k, _ptr(a), lda, _ptr(x))
 
     def gbmv_ptr(self, trans, m, n, kl, ku, alpha, a_addr, lda, x_addr, incx, beta, y_addr, incy):
         return self.L.oracle_dgbmv(trans.encode(), m, n, kl, ku, alpha, a_addr, lda, x_addr, incx, beta, y_addr, incy)
@@ -120,6 +129,18 @@ class _OpenBLASBackend:
         info = i64(0)
         self.L.scipy_dgbtrf_64_(r(i64(m)), r(i64(n)), r(i64(kl)), r(i64(ku)), _ptr(ab), r(i64(ldab)), _ptr(ipiv), r(info))
         return int(info.value)
+
+    def _tb(self, fn, uplo, trans, diag, n, k, a, lda, x):
+        r = C.byref
+        fn(C.c_char_p(uplo.encode()), C.c_char_p(trans.encode()), C.c_char_p(diag.encode()), r(i64(n)), r(i64(k)), _ptr(a),
+           r(i64(lda)), _ptr(x), r(i64(1)), C.c_long(1), C.c_long(1), C.c_long(1))
+        return 0
+
+    def tbsv(self, uplo, trans, diag, n, k, a, lda, x):  # dtbsv_ as src/blas.jl:132-137 calls it
+        return self._tb(self.L.scipy_dtbsv_64_, uplo, trans, diag, n, k, a, lda, x)
+
+    def tbmv(self, uplo, trans, diag, n, k, a, lda, x):  # dtbmv_ as src/blas.jl:94-99 calls it
+        return self._tb(self.L.scipy_dtbmv_64_, uplo, trans, diag, n, k, a, lda, x)
 
     def gbtf2(self, m, n, kl, ku, ab, ldab, ipiv):
         r = C.byref

@@ -271,6 +271,68 @@ int oracle_dgbtrs(char trans, i64 n, i64 kl, i64 ku, i64 nrhs, const double *ab,
     return 0;
 }
 
+/* x <- inv(T)*x, T = banded triangle in BLAS triangular-band storage (tbsv!, src/blas.jl:109-141; reached from
+ * ldiv!(UpperTriangular/LowerTriangular{BandedMatrix}, x), src/tribanded.jl:75-84, and from the back substitution inside
+ * dgbtrs).  'N' only.  Storage (0-based): 'U' T[i,j] at a[(k + i - j) + j*lda], 'L' T[i,j] at a[(i - j) + j*lda].
+ * OpenBLAS driver/level2/tbsv_{U,L}.c: per column, true division by the diagonal (unless unit), then one FMA axpy. */
+int oracle_dtbsv(char uplo, char trans, char diag, i64 n, i64 k, const double *a, i64 lda, double *x)
+{
+    const int up = (uplo == 'U' || uplo == 'u'), unit = (diag == 'U' || diag == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -1;
+    if (!(trans == 'N' || trans == 'n')) return -2;
+    if (!unit && !(diag == 'N' || diag == 'n')) return -3;
+    if (n < 0) return -4;
+    if (k < 0) return -5;
+    if (lda < k + 1) return -7;
+    if (up) {
+        for (i64 j = n - 1; j >= 0; --j) {
+            if (!unit) x[j] = x[j] / a[k + j * lda];
+            const double t = -x[j];
+            for (i64 i = j - 1; i >= imax(0, j - k); --i) x[i] = fma(t, a[(k + i - j) + j * lda], x[i]);
+        }
+    } else {
+        for (i64 j = 0; j < n; ++j) {
+            if (!unit) x[j] = x[j] / a[j * lda];
+            const double t = -x[j];
+            for (i64 i = j + 1; i <= imin(n - 1, j + k); ++i) x[i] = fma(t, a[(i - j) + j * lda], x[i]);
+        }
+    }
+    return 0;
+}
+
+/* x <- T*x (tbmv!, src/blas.jl:71-105; reached from lmul!(UpperTriangular/LowerTriangular{BandedMatrix}, x),
+ * src/tribanded.jl:47-55).  'N' only.  OpenBLAS driver/level2/tbmv_{U,L}.c sweeps the columns (ascending for 'U',
+ * descending for 'L'): x[j] is first axpy'd into the rows it reaches and then scaled by the diagonal, so row i ends as
+ * d_i*x_i (one rounded product; x_i itself if unit) followed by fma(x_j, T[i,j], .) over j = i+1, i+2, ... ('U') or
+ * j = i-1, i-2, ... ('L') with the ORIGINAL x_j. */
+int oracle_dtbmv(char uplo, char trans, char diag, i64 n, i64 k, const double *a, i64 lda, double *x)
+{
+    const int up = (uplo == 'U' || uplo == 'u'), unit = (diag == 'U' || diag == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -1;
+    if (!(trans == 'N' || trans == 'n')) return -2;
+    if (!unit && !(diag == 'N' || diag == 'n')) return -3;
+    if (n < 0) return -4;
+    if (k < 0) return -5;
+    if (lda < k + 1) return -7;
+    if (n == 0) return 0;
+    double *y = (double *)malloc((size_t)n * sizeof(double));
+    if (!y) return -100;
+    for (i64 i = 0; i < n; ++i) {
+        double acc;
+        if (up) {
+            acc = unit ? x[i] : x[i] * a[k + i * lda];
+            for (i64 j = i + 1; j <= imin(n - 1, i + k); ++j) acc = fma(x[j], a[(k + i - j) + j * lda], acc);
+        } else {
+            acc = unit ? x[i] : x[i] * a[i * lda];
+            for (i64 j = i - 1; j >= imax(0, i - k); --j) acc = fma(x[j], a[(i - j) + j * lda], acc);
+        }
+        y[i] = acc;
+    }
+    memcpy(x, y, (size_t)n * sizeof(double));
+    free(y);
+    return 0;
+}
+
 /* banded_mul! triple loop (src/generic/matmul.jl:143-172): the semantic definition of
  * banded x banded used as a second, independent check of oracle_gbmm.  C gets zeros in bands
  * beyond (Al+Bl, Au+Bu).  Band widths may exceed the matrix size; all must be >= 0 here. */

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+exec > gpurun_out/tb.log 2>&1
+set -x
+timeout 900 python -m pytest tests/test_gpu_tb.py -m gpu -x -q 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_gpu_lu.py -m gpu -x -q -k "wide_band_dominant or laplacian" 2>&1 | tail -3
