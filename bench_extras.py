@@ -121,6 +121,19 @@ def cpu_extras(L, cores):
     tf, ts = lu_solve(ns, 1024, 1024, 1, dominant=True)
     out["C5"] = {"sample": "n=2^14 of 2^20 columns, l=u=1024, diagonally dominant, 1 RHS", "lu_sample_ms": round(tf, 1), "solve_sample_ms": round(ts, 1),
                  "lu_full_ms_extrapolated": round(tf * full / ns, 1), "solve_full_ms_extrapolated": round(ts * full / ns, 1)}
+    # triangular band: dtbsv_/dtbmv_ 'U','N','N', k=1024 on n=2^16 of 2^20 columns (1 thread: OpenBLAS' level-2 band
+    # kernels are not threaded at these sizes), linear in n
+    ns, full, k = 1 << 16, 1 << 20, 1024
+    a = np.asfortranarray(rng.random((k + 1, ns))) / (2 * k)
+    a[k, :] = 2.0
+    xv = np.ones(ns)
+    L.drv_tb.restype = dbl
+    L.drv_tb.argtypes = [C.c_int, C.c_char, C.c_char, i64, i64, vp, i64, vp]
+    L.drv_set_threads(1)
+    t_sv = L.drv_tb(0, b"U", b"N", ns, k, a.ctypes.data, k + 1, xv.ctypes.data)
+    t_mv = L.drv_tb(1, b"U", b"N", ns, k, a.ctypes.data, k + 1, xv.ctypes.data)
+    out["TB"] = {"sample": "n=2^16 of 2^20 columns, k=1024, 1 thread", "tbsv_sample_ms": round(1e3 * t_sv, 1), "tbmv_sample_ms": round(1e3 * t_mv, 1),
+                 "tbsv_full_ms_extrapolated": round(1e3 * t_sv * full / ns, 1), "tbmv_full_ms_extrapolated": round(1e3 * t_mv * full / ns, 1)}
     return out
 
 
@@ -178,4 +191,15 @@ def run_extras(bm, c3_n=1 << 22, c4_n=1 << 20, c4_rhs=256):
     del F, X, Bm, W, A
     torch.cuda.empty_cache()
     out["C5"] = run_c5(bm, 1024)
+    # ---- triangular band: the Gauss-Seidel half of examples/finitedifference_2d.jl:18-26 at C5 size ----
+    N = 1024
+    A = laplacian(bm, N)
+    n = N * N
+    b = torch.ones(n, dtype=torch.float64, device="cuda")
+    x = b.clone()
+    t_sv = _time(lambda: bm.ldiv_tri_("U", False, A, x), reps=2, setup=lambda: x.copy_(b))
+    t_mv = _time(lambda: bm.lmul_tri_("U", False, A, x), reps=2, setup=lambda: x.copy_(b))
+    by = 8.0 * n * (N + 1) + 16.0 * n
+    out["TB"] = {"n": n, "k": N, "tbsv_U_ms": round(t_sv, 2), "tbmv_U_ms": round(t_mv, 3), "tbmv_GBs": round(by / t_mv / 1e6, 1),
+                 "algorithmic_bytes": by}
     return out

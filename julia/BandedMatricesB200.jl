@@ -121,3 +121,20 @@ function LAPACK.gbtrs!(trans::AbstractChar, kl::Integer, ku::Integer, m::Integer
 end
 
 end # module
+
+# ---- triangular band solve / multiply: shadow tbsv! / tbmv! (src/blas.jl:121-141, :83-101), reached from ldiv! / lmul! of
+# ---- UpperTriangular / LowerTriangular{<:BandedMatrix} (src/tribanded.jl:47-84); `A` is bandeddata of the triangular view,
+# ---- i.e. a row-range view of the parent's device data array (stride(A,2) = l+u+1).  trans = 'N' only.
+const DBandData = Union{DMat,SubArray{Float64,2,<:DMat}}
+for (jl, sym) in ((:tbsv!, :bmb200_dtbsv), (:tbmv!, :bmb200_dtbmv))
+    @eval function BandedMatrices.$jl(uplo::AbstractChar, trans::AbstractChar, diag::AbstractChar, m::Int, k::Int, A::DBandData, x::DVec)
+        n = size(A, 2)
+        size(A, 1) ≥ k + 1 || throw(ArgumentError("triangular banded data missing"))
+        n == m || throw(DimensionMismatch("matrix is not square: dimensions are $n, $m"))
+        n == length(x) || throw(DimensionMismatch("size of A is $n != length(x) = $(length(x))"))
+        n == 0 && return x
+        chk(ccall(($(QuoteNode(sym)), libbmb200), Cint, (Handle, UInt8, UInt8, UInt8, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+                  handle(), uplo, trans, diag, m, k, pointer(A), max(1, stride(A, 2)), pointer(x), stride(x, 1)), $(string(jl)))
+        x
+    end
+end

@@ -24,6 +24,8 @@ typedef void (*gbmv_t)(const char *, const i64 *, const i64 *, const i64 *, cons
 typedef void (*gbtrf_t)(const i64 *, const i64 *, const i64 *, const i64 *, double *, const i64 *, i64 *, i64 *);
 typedef void (*gbtrs_t)(const char *, const i64 *, const i64 *, const i64 *, const i64 *, const double *,
                         const i64 *, const i64 *, double *, const i64 *, i64 *, long);
+typedef void (*tb_t)(const char *, const char *, const char *, const i64 *, const i64 *, const double *, const i64 *, double *,
+                     const i64 *, long, long, long);
 typedef void (*setthr_t)(int);
 
 static void *lib;
@@ -31,6 +33,7 @@ static gbmv_t f_gbmv;
 static gbtrf_t f_gbtrf;
 static gbtrs_t f_gbtrs;
 static setthr_t f_setthr;
+static tb_t f_tbsv, f_tbmv;
 
 static double now(void)
 {
@@ -48,7 +51,9 @@ int drv_open(const char *path)
     f_gbtrf = (gbtrf_t)dlsym(lib, "scipy_dgbtrf_64_");
     f_gbtrs = (gbtrs_t)dlsym(lib, "scipy_dgbtrs_64_");
     f_setthr = (setthr_t)dlsym(lib, "scipy_openblas_set_num_threads64_");
-    return (f_gbmv && f_gbtrf && f_gbtrs && f_setthr) ? 0 : -2;
+    f_tbsv = (tb_t)dlsym(lib, "scipy_dtbsv_64_");
+    f_tbmv = (tb_t)dlsym(lib, "scipy_dtbmv_64_");
+    return (f_gbmv && f_gbtrf && f_gbtrs && f_setthr && f_tbsv && f_tbmv) ? 0 : -2;
 }
 
 void drv_set_threads(int k) { f_setthr(k); }
@@ -100,5 +105,14 @@ double drv_gbtrs(i64 n, i64 kl, i64 ku, i64 nrhs, const double *ab, i64 ldab, co
 {
     double t0 = now();
     f_gbtrs("N", &n, &kl, &ku, &nrhs, ab, &ldab, ipiv, b, &ldb, info, 1);
+    return now() - t0;
+}
+
+/* dtbsv_ (which = 0) / dtbmv_ (which = 1), trans 'N', as tbsv! / tbmv! call them (src/blas.jl:94-99, :132-137) */
+double drv_tb(int which, char uplo, char diag, i64 n, i64 k, const double *a, i64 lda, double *x)
+{
+    const i64 one = 1;
+    double t0 = now();
+    (which ? f_tbmv : f_tbsv)(&uplo, "N", &diag, &n, &k, a, &lda, x, &one, 1, 1, 1);
     return now() - t0;
 }
