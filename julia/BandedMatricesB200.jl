@@ -120,7 +120,6 @@ function LAPACK.gbtrs!(trans::AbstractChar, kl::Integer, ku::Integer, m::Integer
     B
 end
 
-end # module
 
 # ---- triangular band solve / multiply: shadow tbsv! / tbmv! (src/blas.jl:121-141, :83-101), reached from ldiv! / lmul! of
 # ---- UpperTriangular / LowerTriangular{<:BandedMatrix} (src/tribanded.jl:47-84); `A` is bandeddata of the triangular view,
@@ -138,3 +137,5 @@ for (jl, sym) in ((:tbsv!, :bmb200_dtbsv), (:tbmv!, :bmb200_dtbmv))
         x
     end
 end
+
+end # module
