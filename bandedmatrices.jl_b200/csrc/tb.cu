@@ -31,6 +31,61 @@ tbmv_rows(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda,
     }
 }
 
+// Wide bands: a warp owns 32 consecutive rows (lane = row) and sweeps the columns they reach; for a fixed column the 32 lanes
+// read 32 consecutive band entries (one coalesced 256-byte request) and x[j] is a broadcast.  Each row still accumulates in
+// OpenBLAS' order (j ascending for 'U', descending for 'L').  Eight columns of loads are in flight per warp.
+__global__ void __launch_bounds__(256)
+tbmv_sweep(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 rb = warp * 32; rb < n; rb += nwarps * 32) {
+        const i64 i = rb + lane;
+        const bool live = i < n;
+        double acc = live ? x[i] : 0.0;
+        if (up) {
+            if (live && !unit) acc = __dmul_rn(acc, a[k + i * lda]);
+            const i64 jend = (rb + 31 + k < n - 1) ? rb + 31 + k : n - 1;
+            const double *p = a + k + i;  // T[i,j] = p[j*(lda-1)]
+            for (i64 j0 = rb + 1; j0 <= jend; j0 += 8) {
+                double v[8], xv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const i64 j = j0 + e;
+                    const bool ok = live && j <= jend && j > i && j - i <= k;
+                    v[e] = ok ? ld_stream(p + j * (lda - 1)) : 0.0;
+                    xv[e] = (j <= jend) ? x[j] : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const i64 j = j0 + e;
+                    if (live && j <= jend && j > i && j - i <= k) acc = fma(xv[e], v[e], acc);
+                }
+            }
+        } else {
+            if (live && !unit) acc = __dmul_rn(acc, a[i * lda]);
+            const i64 jbeg = (rb - k > 0) ? rb - k : 0;
+            const double *p = a + i;      // T[i,j] = p[j*(lda-1)]
+            for (i64 j0 = rb + 30; j0 >= jbeg; j0 -= 8) {
+                double v[8], xv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const i64 j = j0 - e;
+                    const bool ok = live && j >= jbeg && j < i && i - j <= k;
+                    v[e] = ok ? ld_stream(p + j * (lda - 1)) : 0.0;
+                    xv[e] = (j >= jbeg) ? x[j] : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const i64 j = j0 - e;
+                    if (live && j >= jbeg && j < i && i - j <= k) acc = fma(xv[e], v[e], acc);
+                }
+            }
+        }
+        if (live) y[i] = acc;
+    }
+}
+
 static int tb_check(char uplo, char trans, char diag, int64_t n, int64_t k, int64_t lda, int64_t incx, int &up, int &unit)
 {
     up = (uplo == 'U' || uplo == 'u');
@@ -79,8 +134,13 @@ extern "C" int bmb200_dtbmv(bmb200_handle_t h, char uplo, char trans, char diag,
     DeviceGuard g(h->device);
     if (bmb_ensure_scratch(h, (size_t)n * sizeof(double)) != 0) return BMB200_ERR_CUDA;
     double *y = (double *)h->scratch;
-    const i64 blocks = imin64(cdiv64(n, 256), (i64)h->sm_count * 16);
-    tbmv_rows<<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, y);
+    if (k >= 16) {
+        const i64 blocks = imin64(cdiv64(n, 32 * 8), (i64)h->sm_count * 8);
+        tbmv_sweep<<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, y);
+    } else {
+        const i64 blocks = imin64(cdiv64(n, 256), (i64)h->sm_count * 16);
+        tbmv_rows<<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, y);
+    }
     BMB_LAUNCH_CHECK(h);
     BMB_CUDA(h, cudaMemcpyAsync(dx, y, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     return 0;

@@ -17,6 +17,8 @@ timeout 600 $NCU --set full --import-source on -k regex:gbmm_bb_dmma -s 1 -c 1 -
 ncu -i gpurun_out/gbmm_c3_full.ncu-rep --page raw --csv > gpurun_out/gbmm_c3_raw.csv 2>/dev/null
 timeout 900 $NCU --set full -k regex:gbtrf_pipe_kernel -s 1 -c 1 -o gpurun_out/pipe_full -f python tools/prof_case.py widelu 16384 1024 dom > gpurun_out/ncu_pipe.log 2>&1
 ncu -i gpurun_out/pipe_full.ncu-rep --page raw --csv > gpurun_out/pipe_raw.csv 2>/dev/null
+timeout 900 $NCU --set full -k regex:gbtrs_cluster -s 1 -c 1 -o gpurun_out/cluster_full -f python tools/prof_case.py widelu 16384 1024 dom > gpurun_out/ncu_cluster.log 2>&1
+ncu -i gpurun_out/cluster_full.ncu-rep --page raw --csv > gpurun_out/cluster_raw.csv 2>/dev/null
 timeout 900 $NCU --metrics gpu__time_duration.sum -c 200 --csv --log-file gpurun_out/launches_c5.csv python tools/prof_case.py widelu 65536 1024 dom > gpurun_out/ncu_c5.log 2>&1
 rm -f gpurun_out/*.ncu-rep
 ls -la gpurun_out
