@@ -8,7 +8,7 @@ timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -2
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 900 gpurun_out/bench_ref.json
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 2500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
-timeout 900 python bench.py --extras --no-e2e --no-cpu --steps 5 > gpurun_out/bench_extras.json 2> gpurun_out/bench_extras.err; tail -c 1300 gpurun_out/bench_extras.json
+timeout 900 python bench.py --extras --no-e2e --steps 5 > gpurun_out/bench_extras.json 2> gpurun_out/bench_extras.err; tail -c 1300 gpurun_out/bench_extras.json
 NCU="ncu --clock-control none"
 timeout 600 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/launches_gbmv_c2.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_bench.log 2>&1
 timeout 600 $NCU --set full --import-source on -k regex:gbmv_n_systolic -s 3 -c 1 -o gpurun_out/gbmv_c2_full -f python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1

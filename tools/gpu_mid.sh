@@ -4,4 +4,4 @@ mkdir -p gpurun_out
 exec > gpurun_out/mid.log 2>&1
 set -x
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 900 python bench.py --extras --no-e2e --no-cpu --steps 5 > gpurun_out/bench_extras.json 2> gpurun_out/bench_extras.err; tail -c 1500 gpurun_out/bench_extras.json; tail -3 gpurun_out/bench_extras.err
+timeout 900 python bench.py --extras --no-e2e --steps 5 > gpurun_out/bench_extras.json 2> gpurun_out/bench_extras.err; tail -c 1500 gpurun_out/bench_extras.json; tail -3 gpurun_out/bench_extras.err
