@@ -33,54 +33,85 @@ tbmv_rows(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda,
 
 // Wide bands: a warp owns 32 consecutive rows (lane = row) and sweeps the columns they reach; for a fixed column the 32 lanes
 // read 32 consecutive band entries (one coalesced 256-byte request) and x[j] is a broadcast.  Each row still accumulates in
-// OpenBLAS' order (j ascending for 'U', descending for 'L').  Eight columns of loads are in flight per warp.
+// OpenBLAS' order (j ascending for 'U', descending for 'L').  Columns go in chunks of 8; the next chunk's loads are issued
+// before the current chunk's FMA chain (register double buffer), and chunks that lie inside the band for all 32 rows -- all
+// but ~40 columns per row block -- run without any predicate.
+template <bool UP>
+__device__ __forceinline__ bool tbmv_load8(const double *__restrict__ p, i64 st, const double *__restrict__ x, i64 j0, i64 lo_all, i64 hi_all,
+                                           i64 jlo, i64 jhi, i64 i, int k, bool live, double (&v)[8], double (&xv)[8])
+{
+    // chunk columns: UP j0 .. j0+7, else j0 .. j0-7;  [lo_all, hi_all] = columns every one of the 32 rows reaches
+    const i64 ja = UP ? j0 : j0 - 7, jb = UP ? j0 + 7 : j0;
+    if (ja >= lo_all && jb <= hi_all) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const i64 j = UP ? j0 + e : j0 - e;
+            v[e] = ld_stream(p + j * st);
+            xv[e] = x[j];
+        }
+        return true;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const i64 j = UP ? j0 + e : j0 - e;
+        const bool inr = j >= jlo && j <= jhi;
+        const bool ok = live && inr && (UP ? (j > i && j - i <= k) : (j < i && i - j <= k));
+        v[e] = ok ? ld_stream(p + j * st) : 0.0;
+        xv[e] = inr ? x[j] : 0.0;
+    }
+    return false;
+}
+template <bool UP>
+__device__ __forceinline__ double tbmv_fma8(double acc, bool full, i64 j0, i64 jlo, i64 jhi, i64 i, int k, bool live, const double (&v)[8],
+                                            const double (&xv)[8])
+{
+    if (full) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = fma(xv[e], v[e], acc);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const i64 j = UP ? j0 + e : j0 - e;
+            if (live && j >= jlo && j <= jhi && (UP ? (j > i && j - i <= k) : (j < i && i - j <= k))) acc = fma(xv[e], v[e], acc);
+        }
+    }
+    return acc;
+}
+
+template <bool UP>
 __global__ void __launch_bounds__(256)
-tbmv_sweep(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda, const double *__restrict__ x, double *__restrict__ y)
+tbmv_sweep(i64 n, int k, int unit, const double *__restrict__ a, i64 lda, const double *__restrict__ x, double *__restrict__ y)
 {
     const int lane = threadIdx.x & 31;
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const i64 st = lda - 1;
     for (i64 rb = warp * 32; rb < n; rb += nwarps * 32) {
         const i64 i = rb + lane;
         const bool live = i < n;
         double acc = live ? x[i] : 0.0;
-        if (up) {
-            if (live && !unit) acc = __dmul_rn(acc, a[k + i * lda]);
-            const i64 jend = (rb + 31 + k < n - 1) ? rb + 31 + k : n - 1;
-            const double *p = a + k + i;  // T[i,j] = p[j*(lda-1)]
-            for (i64 j0 = rb + 1; j0 <= jend; j0 += 8) {
-                double v[8], xv[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const i64 j = j0 + e;
-                    const bool ok = live && j <= jend && j > i && j - i <= k;
-                    v[e] = ok ? ld_stream(p + j * (lda - 1)) : 0.0;
-                    xv[e] = (j <= jend) ? x[j] : 0.0;
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const i64 j = j0 + e;
-                    if (live && j <= jend && j > i && j - i <= k) acc = fma(xv[e], v[e], acc);
-                }
-            }
-        } else {
-            if (live && !unit) acc = __dmul_rn(acc, a[i * lda]);
-            const i64 jbeg = (rb - k > 0) ? rb - k : 0;
-            const double *p = a + i;      // T[i,j] = p[j*(lda-1)]
-            for (i64 j0 = rb + 30; j0 >= jbeg; j0 -= 8) {
-                double v[8], xv[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const i64 j = j0 - e;
-                    const bool ok = live && j >= jbeg && j < i && i - j <= k;
-                    v[e] = ok ? ld_stream(p + j * (lda - 1)) : 0.0;
-                    xv[e] = (j >= jbeg) ? x[j] : 0.0;
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const i64 j = j0 - e;
-                    if (live && j >= jbeg && j < i && i - j <= k) acc = fma(xv[e], v[e], acc);
-                }
-            }
+        if (live && !unit) acc = __dmul_rn(acc, a[(UP ? k : 0) + i * lda]);
+        // T[i,j] = p[j*(lda-1)] with p = a + (UP ? k : 0) + i
+        const double *p = a + (UP ? k : 0) + i;
+        // columns reached by the block [jlo, jhi]; by all 32 rows (only if all 32 rows exist) [lo_all, hi_all]
+        const i64 jlo = UP ? rb + 1 : ((rb - k > 0) ? rb - k : 0);
+        const i64 jhi = UP ? ((rb + 31 + k < n - 1) ? rb + 31 + k : n - 1) : rb + 30;
+        const bool all = rb + 31 < n;
+        const i64 lo_all = all ? (UP ? rb + 32 : ((rb + 31 - k > 0) ? rb + 31 - k : 0)) : 1;
+        const i64 hi_all = all ? (UP ? ((rb + k < n - 1) ? rb + k : n - 1) : rb - 1) : 0;
+        if (jlo > jhi) { if (live) y[i] = acc; continue; }
+        const i64 nch = (jhi - jlo) / 8 + 1;
+        double va[8], xa[8], vb[8], xb[8];
+        bool fa, fb = false;
+        i64 j0 = UP ? jlo : jhi;
+        fa = tbmv_load8<UP>(p, st, x, j0, lo_all, hi_all, jlo, jhi, i, k, live, va, xa);
+        for (i64 c = 0; c < nch; c += 2) {
+            const i64 j1 = UP ? j0 + 8 : j0 - 8;
+            if (c + 1 < nch) fb = tbmv_load8<UP>(p, st, x, j1, lo_all, hi_all, jlo, jhi, i, k, live, vb, xb);
+            acc = tbmv_fma8<UP>(acc, fa, j0, jlo, jhi, i, k, live, va, xa);
+            const i64 j2 = UP ? j1 + 8 : j1 - 8;
+            if (c + 2 < nch) fa = tbmv_load8<UP>(p, st, x, j2, lo_all, hi_all, jlo, jhi, i, k, live, va, xa);
+            if (c + 1 < nch) acc = tbmv_fma8<UP>(acc, fb, j1, jlo, jhi, i, k, live, vb, xb);
+            j0 = j2;
         }
         if (live) y[i] = acc;
     }
@@ -136,7 +167,8 @@ extern "C" int bmb200_dtbmv(bmb200_handle_t h, char uplo, char trans, char diag,
     double *y = (double *)h->scratch;
     if (k >= 16) {
         const i64 blocks = imin64(cdiv64(n, 32 * 8), (i64)h->sm_count * 8);
-        tbmv_sweep<<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, y);
+        if (up) tbmv_sweep<true><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, unit, dA, lda, dx, y);
+        else tbmv_sweep<false><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, unit, dA, lda, dx, y);
     } else {
         const i64 blocks = imin64(cdiv64(n, 256), (i64)h->sm_count * 16);
         tbmv_rows<<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, y);

@@ -2,5 +2,6 @@
 mkdir -p gpurun_out
 exec > gpurun_out/tb.log 2>&1
 set -x
-timeout 900 python -m pytest tests/test_gpu_tb.py -m gpu -x -q 2>&1 | tail -15
-timeout 600 python -m pytest tests/test_gpu_lu.py -m gpu -x -q -k "wide_band_dominant or laplacian" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_tb.py -m gpu -x -q 2>&1 | tail -5
+timeout 300 python tools/time_tb.py 1048576 1024
+timeout 300 python tools/time_tb.py 4194304 64
