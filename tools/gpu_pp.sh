@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 ./tools/pingpong > gpurun_out/pingpong.log 2>&1
+timeout 120 ./tools/dmma_lat > gpurun_out/dmma_lat.log 2>&1
