@@ -85,6 +85,27 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// Flat staging of `ncols` whole band columns that are contiguous in global memory (ld == W) into the padded shared layout
+// (pitch P): the slab is walked element by element by the whole CTA with an incrementally maintained (column, row), ~10 issued
+// instructions per 32 elements -- the per-column loop (64-bit column address, row-range tests, a 3rd trip for row 64 alone) cost
+// ~85 per 65-element column, and warp-stall sampling put 35-40 % of this kernel's time there.
+__device__ __forceinline__ void gm_stage_flat(double *dst0, int P, const double *src, int W, int ncols, int tid, int nthreads)
+{
+    const int total = ncols * W;
+    int col = tid / W, row = tid - col * W;
+    const int dc = nthreads / W, dr = nthreads - dc * W;
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst0) + 8u * (unsigned)(col * P + row);
+    const unsigned dstep = 8u * (unsigned)(dc * P + dr), dwrap = 8u * (unsigned)(P - W);
+    const double *sp = src + tid;
+    for (int e = tid; e < total; e += nthreads) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(sp) : "memory");
+        sp += nthreads;
+        d += dstep;
+        row += dr;
+        if (row >= W) { row -= W; d += dwrap; }
+    }
+}
+
 // GM_NT = row tiles (of 8) per work item: the V range of an item is the union over its tiles, so a tall item spends
 // most of its predicated DMMA slots outside the band parallelogram (9 tiles: 44 % of the slots live; 3 tiles: 77 %).
 template <int GM_NT>
@@ -109,7 +130,12 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
         const i64 j0 = tile * GM_TJ;
         const i64 vbase = 4 * floordiv(j0 - Bu, 4);  // first staged A column (aligned to the k step)
         // ---- stage A columns [vbase, vbase+NA) and B columns [j0, j0+TJ): asynchronous copies, all in flight ----
-        for (int s = wid; s < NA; s += GM_THREADS / 32) {
+        // interior tiles (every staged column complete and inside the matrix, columns contiguous): flat slab copy
+        const bool flatA = lda == WA && vbase >= Au && vbase + NA <= nu && vbase + NA - 1 + Al <= n - 1;
+        const bool flatB = ldb == WB && j0 >= Bu && j0 + GM_TJ <= mcols && j0 + GM_TJ - 1 + Bl <= nu - 1;
+        if (flatA) gm_stage_flat(As + GM_PAD, PA, a + vbase * lda, WA, NA, tid, GM_THREADS);
+        if (flatB) gm_stage_flat(Bs + GM_PAD, PB, b + j0 * ldb, WB, GM_TJ, tid, GM_THREADS);
+        for (int s = wid; s < (flatA ? 0 : NA); s += GM_THREADS / 32) {
             const i64 v = vbase + s;
             double *dst = As + (size_t)s * PA + GM_PAD;
             int rlo = 1, rhi = 0;  // band rows r with 0 <= v - Au + r < n
@@ -127,7 +153,7 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
                 }
             }
         }
-        for (int s = wid; s < GM_TJ; s += GM_THREADS / 32) {
+        for (int s = wid; s < (flatB ? 0 : GM_TJ); s += GM_THREADS / 32) {
             const i64 j = j0 + s;
             double *dst = Bs + (size_t)s * PB + GM_PAD;
             int rlo = 1, rhi = 0;  // band rows r with 0 <= j - Bu + r < nu
