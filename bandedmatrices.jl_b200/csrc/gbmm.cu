@@ -263,8 +263,7 @@ gbmm_bb_dmma(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
 // tile's B columns, double-buffered) are fetched, with cp.async, while the tensor cores work on the current tile.
 // One persistent CTA per SM, 16 warps; per-element operation order unchanged => bit-identical results.
 // ------------------------------------------------------------------------------------------------
-#define GR_THREADS 512
-template <int GM_NT>
+template <int GM_NT, int GR_THREADS>
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gbmm_bb_ring(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, int Cu, double alpha,
              const double *__restrict__ a, i64 lda, const double *__restrict__ b, i64 ldb, double beta,
@@ -284,6 +283,13 @@ gbmm_bb_ring(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
     __syncthreads();
     const i64 vorg = 4 * floordiv(t_begin * TJ - Bu, 4);  // ring origin: column v lives in slot (v - vorg) mod RS
     auto stageA = [&](i64 vfirst, int ncols) {
+        if (ncols >= 16 && lda == WA && vfirst >= Au && vfirst + ncols <= nu && vfirst + ncols - 1 + Al <= n - 1) {  // interior: flat slab copy
+            const int slot0 = (int)((unsigned)(vfirst - vorg) % (unsigned)RS);
+            const int n1 = (RS - slot0 < ncols) ? RS - slot0 : ncols;                                  // columns before the ring wraps
+            gm_stage_flat(As + (size_t)slot0 * PA + GM_PAD, PA, a + vfirst * lda, WA, n1, tid, GR_THREADS);
+            if (n1 < ncols) gm_stage_flat(As + GM_PAD, PA, a + (vfirst + n1) * lda, WA, ncols - n1, tid, GR_THREADS);
+            return;
+        }
         for (int s = wid; s < ncols; s += NW) {
             const i64 v = vfirst + s;
             double *dst = As + (size_t)((unsigned)(v - vorg) % (unsigned)RS) * PA + GM_PAD;
@@ -304,6 +310,10 @@ gbmm_bb_ring(i64 n, i64 nu, i64 mcols, int Al, int Au, int Bl, int Bu, int Cl, i
         }
     };
     auto stageB = [&](double *Bs, i64 j0) {
+        if (TJ >= 16 && ldb == WB && j0 >= Bu && j0 + TJ <= mcols && j0 + TJ - 1 + Bl <= nu - 1) {
+            gm_stage_flat(Bs + GM_PAD, PB, b + j0 * ldb, WB, TJ, tid, GR_THREADS);
+            return;
+        }
         for (int s = wid; s < TJ; s += NW) {
             const i64 j = j0 + s;
             double *dst = Bs + (size_t)s * PB + GM_PAD;
@@ -497,15 +507,18 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
             const i64 tpc = cdiv64(ntiles, blocks);
             if (tpc * TJ + Bl + Bu + 64 >= ((i64)1 << 31)) break;
             static const int rnt = getenv("BMB200_GBMM_NT") ? atoi(getenv("BMB200_GBMM_NT")) : 3;  // tuning switch
-#define GR_LAUNCH(NT)                                                                                                                  \
+#define GR_LAUNCH(NT, TH)                                                                                                              \
     do {                                                                                                                               \
-        BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_ring<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));                 \
-        gbmm_bb_ring<NT><<<(unsigned)cdiv64(ntiles, tpc), GR_THREADS, smem_r, h->stream>>>(n, nu, mprod, (int)Al, (int)Au, (int)Bl,    \
-                                                                                           (int)Bu, (int)Cl, (int)Cu, alpha, dA, lda, \
-                                                                                           dB, ldb, beta, dC, ldc, PA, PB, NAr, RS,   \
-                                                                                           TJ, ntiles, tpc);                          \
+        BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_ring<NT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));             \
+        gbmm_bb_ring<NT, TH><<<(unsigned)cdiv64(ntiles, tpc), TH, smem_r, h->stream>>>(n, nu, mprod, (int)Al, (int)Au, (int)Bl,        \
+                                                                                       (int)Bu, (int)Cl, (int)Cu, alpha, dA, lda,     \
+                                                                                       dB, ldb, beta, dC, ldc, PA, PB, NAr, RS,       \
+                                                                                       TJ, ntiles, tpc);                              \
     } while (0)
-            if (rnt == 2) GR_LAUNCH(2); else if (rnt == 4) GR_LAUNCH(4); else if (rnt == 6) GR_LAUNCH(6); else GR_LAUNCH(3);
+            static const int rw_env = getenv("BMB200_GBMM_RW") ? atoi(getenv("BMB200_GBMM_RW")) : 0;  // warps per CTA (tuning switch)
+            const int rw = rw_env ? rw_env : (TJ >= 16 ? 16 : 12);
+            if (rw == 12) { if (rnt == 2) GR_LAUNCH(2, 384); else GR_LAUNCH(3, 384); }
+            else { if (rnt == 2) GR_LAUNCH(2, 512); else GR_LAUNCH(3, 512); }
 #undef GR_LAUNCH
             BMB_LAUNCH_CHECK(h);
             jsplit = mprod;
