@@ -6,15 +6,15 @@
 // One SM can pull only ~64 B/clk of factor entries out of L2, which bounded the single-CTA kernel (6 us per 16-column
 // panel at l=u=1024).  Here the band is cut, per 16-row block, into a NEAR part (the GC_D row blocks next to the
 // diagonal block) and a FAR part:
-//   * the LEADER CTA (cluster rank 0) owns the dependency chain.  Warp w takes the 16-row blocks t = w, w+8, ...: it
+//   * the LEADER CTA (cluster rank 0) owns the dependency chain.  Warp w takes the 16-row blocks t = w, w+GC_LW, ...: it
 //     receives the block from a worker (hand-off ring in its shared memory), applies the updates of the last GC_D
 //     panels as their solutions appear, solves the 16 x 16 diagonal triangle with shuffles, publishes the 16 solution
-//     entries in its own shared memory (next warp's input), in global memory (the result) and in every worker's shared
-//     memory (DSMEM stores + release flag).
-//   * the WORKER CTAs (ranks 1..C-1) stream the far part of the factors.  A half-warp owns one 16-row block from its
+//     entries in its own shared memory (next warp's input: plain doubles, CTA fence, tag), in global memory (the result)
+//     and in every worker's shared memory (DSMEM stores of self-validating 16-byte cells, no flags or fences).
+//   * the WORKER CTAs (ranks 1..C-1) stream the far part of the factors.  A warp owns two 16-row blocks from their
 //     birth (load of b) through all far panels (distance kl/16 .. GC_D+1 blocks from the diagonal), one row per lane,
-//     16 FMAs per panel, and then hands the 16 values to the leader.  Factor loads for a panel are issued before the
-//     wait for that panel's solution, so they are in flight while the chain is busy.
+//     16 FMAs per panel, and then hands the values to the leader.  The next panel's factor entries are loaded before the
+//     wait for the current panel's solution (register double buffer), so they are in flight while the chain is busy.
 // Per element the operations and their order are exactly those of DGBTRS 'N' (SURVEY.md A.4): forward
 // b[i] = fma(-b[j], L[i,j], b[i]) for j ascending; backward b[j] = b[j] / U[j,j] (true quotient, gb_div), then
 // b[i] = fma(-b[j], U[i,j], b[i]) for j descending; entries outside the band or the matrix are skipped, not multiplied
