@@ -2,7 +2,7 @@
 // from ldiv!/lmul! of UpperTriangular / LowerTriangular{<:BandedMatrix} (src/tribanded.jl:47-84).  SURVEY.md 8(f) rank 2:
 // the same sweeps as the back substitution inside gbtrs, exposed on BLAS triangular-band storage
 //   'U': T[i,j] at a[(k + i - j) + j*lda]      'L': T[i,j] at a[(i - j) + j*lda]        (0-based, i - j within the band)
-// trans = 'N' only (the reference uses 'T' for row-major layouts only; not built here).  incx must be 1.
+// trans = 'N' and 'T'/'C' (the reference reaches 'T' through row-major layouts, src/tribanded.jl:86-96).  incx must be 1.
 //   * bmb200_dtbsv: the cluster pipeline of gbtrs_cluster.cu, one sweep (OpenBLAS tbsv_{U,L}: true division by the
 //     diagonal unless unit, then fma(-x_j, T[i,j], x_i)) => bit-identical to the reference CPU path.
 //   * bmb200_dtbmv: one thread per row, d_i*x_i (x_i if unit) then fma(x_j, T[i,j], .) over j ascending ('U') or
@@ -117,12 +117,79 @@ tbmv_sweep(i64 n, int k, int unit, const double *__restrict__ a, i64 lda, const 
     }
 }
 
+// ---- trans = 'T': op(T) = T^T.  Every column of the band array is now a ROW of the operator: a dot product of contiguous
+// band entries with a window of x.  OpenBLAS uses its SIMD dot kernel here (summation order unspecified), so these are compared
+// to the oracle at 1e-13 like the other transposed paths, not bit for bit. ----
+// tbmv 'T': one warp per column, lanes stride the contiguous column, shuffle reduction.
+__global__ void __launch_bounds__(256)
+tbmv_t_cols(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 j = warp; j < n; j += nwarps) {
+        // 'U': rows j-k..j-1 live at a[k-(j-i) + j*lda]; 'L': rows j+1..j+k at a[(i-j) + j*lda]
+        const i64 i0 = up ? ((j - k > 0) ? j - k : 0) : j + 1, i1 = up ? j - 1 : ((j + k < n - 1) ? j + k : n - 1);
+        const double *col = a + j * lda + (up ? k - j : -j);  // T[i,j] = col[i]
+        double acc = 0.0;
+        for (i64 i = i0 + lane; i <= i1; i += 32) acc = fma(ld_stream(col + i), x[i], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[j] = (unit ? x[j] : __dmul_rn(x[j], a[(up ? k : 0) + j * lda])) + acc;
+    }
+}
+
+// tbsv 'T': a chain of n dependent dot products, one warp: x_j = (x_j - sum_i T[i,j] x_i) / T[j,j], j ascending for 'U'
+// (T^T is lower triangular), descending for 'L'.  The solved entries the next columns need stay in a shared-memory ring; the
+// band entries of the next column are loaded (they do not depend on x) before the current column's reduction.
+template <int KPL>  // band entries per lane: 32*KPL >= k
+__global__ void __launch_bounds__(32)
+tbsv_t_chain(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda, double *__restrict__ x, int ring)
+{
+    extern __shared__ double xr[];  // ring of solved entries, indexed by matrix row & (ring-1)
+    const int lane = threadIdx.x, M = ring - 1;
+    auto colptr = [&](i64 j) { return a + j * lda + (up ? k : 0); };  // diagonal entry of column j
+    auto load_col = [&](i64 j, double (&v)[KPL]) {
+        // entry e = 1..k of column j pairs with row j-e ('U') / j+e ('L'); lane handles e = 1 + lane + 32*q
+        const double *d = colptr(j);
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const int e = 1 + lane + 32 * q;
+            const i64 r = up ? j - e : j + e;
+            v[q] = (e <= k && r >= 0 && r < n) ? ld_stream(up ? d - e : d + e) : 0.0;
+        }
+    };
+    double v[KPL], vn[KPL];
+    i64 j = up ? 0 : n - 1;
+    const i64 step = up ? 1 : -1;
+    load_col(j, v);
+    for (i64 c = 0; c < n; ++c, j += step) {
+        const i64 jn = j + step;
+        if (c + 1 < n) load_col(jn, vn);
+        const double dj = unit ? 1.0 : colptr(j)[0];
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const int e = 1 + lane + 32 * q;
+            const i64 r = up ? j - e : j + e;
+            if (e <= k && r >= 0 && r < n) acc = fma(v[q], xr[(int)(r & M)], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        double xj = x[j] - acc;
+        if (!unit) xj = xj / dj;
+        if (lane == 0) { xr[(int)(j & M)] = xj; x[j] = xj; }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) v[q] = vn[q];
+    }
+}
+
 static int tb_check(char uplo, char trans, char diag, int64_t n, int64_t k, int64_t lda, int64_t incx, int &up, int &unit)
 {
     up = (uplo == 'U' || uplo == 'u');
     unit = (diag == 'U' || diag == 'u');
     if (!up && !(uplo == 'L' || uplo == 'l')) return -2;
-    if (!(trans == 'N' || trans == 'n')) return -3;  // 'T' / 'C' (row-major layouts in the reference): not built
+    if (!(trans == 'N' || trans == 'n' || trans == 'T' || trans == 't' || trans == 'C' || trans == 'c')) return -3;
     if (!unit && !(diag == 'N' || diag == 'n')) return -4;
     if (n < 0) return -5;
     if (k < 0) return -6;
@@ -141,6 +208,25 @@ extern "C" int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag,
     if (n == 0) return 0;
     if (!dA || !dx) return -7;
     DeviceGuard g(h->device);
+    if (!(trans == 'N' || trans == 'n')) {
+        if (k > 32 * 32) {
+            snprintf(h->err, sizeof(h->err), "dtbsv 'T': band width %lld > 1024 is not supported", (long long)k);
+            return BMB200_ERR_CUDA;
+        }
+        int ring = 64;
+        while (ring < k + 2) ring <<= 1;
+        const size_t smem = (size_t)ring * sizeof(double);
+#define TB_T_LAUNCH(KPL) tbsv_t_chain<KPL><<<1, 32, smem, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, ring)
+        if (k <= 32) TB_T_LAUNCH(1);
+        else if (k <= 64) TB_T_LAUNCH(2);
+        else if (k <= 128) TB_T_LAUNCH(4);
+        else if (k <= 256) TB_T_LAUNCH(8);
+        else if (k <= 512) TB_T_LAUNCH(16);
+        else TB_T_LAUNCH(32);
+#undef TB_T_LAUNCH
+        BMB_LAUNCH_CHECK(h);
+        return 0;
+    }
     // 'U': diagonal in row k of the band array, reach k above it (mode 0 with kl = 0 divides, mode 1 does not);
     // 'L': diagonal in row 0, reach k below it (mode 2 unit, mode 3 dividing)
     const int mode = up ? (unit ? 1 : 0) : (unit ? 2 : 3);
@@ -165,7 +251,10 @@ extern "C" int bmb200_dtbmv(bmb200_handle_t h, char uplo, char trans, char diag,
     DeviceGuard g(h->device);
     if (bmb_ensure_scratch(h, (size_t)n * sizeof(double)) != 0) return BMB200_ERR_CUDA;
     double *y = (double *)h->scratch;
-    if (k >= 16) {
+    if (!(trans == 'N' || trans == 'n')) {
+        const i64 blocks = imin64(cdiv64(n, 8), (i64)h->sm_count * 8);
+        tbmv_t_cols<<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, y);
+    } else if (k >= 16) {
         const i64 blocks = imin64(cdiv64(n, 32 * 8), (i64)h->sm_count * 8);
         if (up) tbmv_sweep<true><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, unit, dA, lda, dx, y);
         else tbmv_sweep<false><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, unit, dA, lda, dx, y);

@@ -113,8 +113,8 @@ int bmb200_dgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t kl, int64_t 
  * Replace dtbsv_ / dtbmv_ reached through tbsv!(uplo, trans, diag, m, k, A, x) (src/blas.jl:109-141) and
  * tbmv!(...) (src/blas.jl:71-105), i.e. ldiv! / lmul! of UpperTriangular / LowerTriangular{<:BandedMatrix}
  * (src/tribanded.jl:47-84).  dA is BLAS triangular-band storage ('U': T[i,j] at dA[(k+i-j) + j*lda],
- * 'L': T[i,j] at dA[(i-j) + j*lda]); dx (n doubles, incx = 1) is overwritten.  trans = 'N' only (-3 otherwise).
- * Results are bit-identical to OpenBLAS dtbsv_/dtbmv_.                                                    */
+ * 'L': T[i,j] at dA[(i-j) + j*lda]); dx (n doubles, incx = 1) is overwritten.  trans 'N': bit-identical to OpenBLAS
+ * dtbsv_/dtbmv_; 'T'/'C' (dot-product forms, k <= 1024 for dtbsv): equal to 1e-13.                                                  */
 int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k,
                  const double *dA, int64_t lda, double *dx, int64_t incx);
 int bmb200_dtbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k,

@@ -123,7 +123,7 @@ end
 
 # ---- triangular band solve / multiply: shadow tbsv! / tbmv! (src/blas.jl:121-141, :83-101), reached from ldiv! / lmul! of
 # ---- UpperTriangular / LowerTriangular{<:BandedMatrix} (src/tribanded.jl:47-84); `A` is bandeddata of the triangular view,
-# ---- i.e. a row-range view of the parent's device data array (stride(A,2) = l+u+1).  trans = 'N' only.
+# ---- i.e. a row-range view of the parent's device data array (stride(A,2) = l+u+1).  trans 'N' and 'T'/'C'.
 const DBandData = Union{DMat,SubArray{Float64,2,<:DMat}}
 for (jl, sym) in ((:tbsv!, :bmb200_dtbsv), (:tbmv!, :bmb200_dtbmv))
     @eval function BandedMatrices.$jl(uplo::AbstractChar, trans::AbstractChar, diag::AbstractChar, m::Int, k::Int, A::DBandData, x::DVec)

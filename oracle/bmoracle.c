@@ -272,18 +272,39 @@ int oracle_dgbtrs(char trans, i64 n, i64 kl, i64 ku, i64 nrhs, const double *ab,
 }
 
 /* x <- inv(T)*x, T = banded triangle in BLAS triangular-band storage (tbsv!, src/blas.jl:109-141; reached from
- * ldiv!(UpperTriangular/LowerTriangular{BandedMatrix}, x), src/tribanded.jl:75-84, and from the back substitution inside
- * dgbtrs).  'N' only.  Storage (0-based): 'U' T[i,j] at a[(k + i - j) + j*lda], 'L' T[i,j] at a[(i - j) + j*lda].
+ * ldiv!(UpperTriangular/LowerTriangular{BandedMatrix}, x), src/tribanded.jl:75-96 ('T' for row-major layouts), and from the
+ * back substitution inside dgbtrs).  Storage (0-based): 'U' T[i,j] at a[(k + i - j) + j*lda], 'L' T[i,j] at a[(i - j) + j*lda].
  * OpenBLAS driver/level2/tbsv_{U,L}.c: per column, true division by the diagonal (unless unit), then one FMA axpy. */
 int oracle_dtbsv(char uplo, char trans, char diag, i64 n, i64 k, const double *a, i64 lda, double *x)
 {
     const int up = (uplo == 'U' || uplo == 'u'), unit = (diag == 'U' || diag == 'u');
+    const int tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
     if (!up && !(uplo == 'L' || uplo == 'l')) return -1;
-    if (!(trans == 'N' || trans == 'n')) return -2;
+    if (!tr && !(trans == 'N' || trans == 'n')) return -2;
     if (!unit && !(diag == 'N' || diag == 'n')) return -3;
     if (n < 0) return -4;
     if (k < 0) return -5;
     if (lda < k + 1) return -7;
+    if (tr) {
+        /* reference-BLAS DTBSV 'T': one dot product per column (OpenBLAS uses a SIMD dot whose order is unspecified, so
+         * 'T' is compared to tolerance, not bits): x_j = (x_j - sum_i T[i,j] x_i) / T[j,j] */
+        if (up) {
+            for (i64 j = 0; j < n; ++j) {
+                double acc = 0.0;
+                for (i64 i = imax(0, j - k); i < j; ++i) acc = fma(a[(k + i - j) + j * lda], x[i], acc);
+                x[j] = x[j] - acc;
+                if (!unit) x[j] = x[j] / a[k + j * lda];
+            }
+        } else {
+            for (i64 j = n - 1; j >= 0; --j) {
+                double acc = 0.0;
+                for (i64 i = imin(n - 1, j + k); i > j; --i) acc = fma(a[(i - j) + j * lda], x[i], acc);
+                x[j] = x[j] - acc;
+                if (!unit) x[j] = x[j] / a[j * lda];
+            }
+        }
+        return 0;
+    }
     if (up) {
         for (i64 j = n - 1; j >= 0; --j) {
             if (!unit) x[j] = x[j] / a[k + j * lda];
@@ -301,15 +322,16 @@ int oracle_dtbsv(char uplo, char trans, char diag, i64 n, i64 k, const double *a
 }
 
 /* x <- T*x (tbmv!, src/blas.jl:71-105; reached from lmul!(UpperTriangular/LowerTriangular{BandedMatrix}, x),
- * src/tribanded.jl:47-55).  'N' only.  OpenBLAS driver/level2/tbmv_{U,L}.c sweeps the columns (ascending for 'U',
+ * src/tribanded.jl:47-55).  OpenBLAS driver/level2/tbmv_{U,L}.c ('N') sweeps the columns (ascending for 'U',
  * descending for 'L'): x[j] is first axpy'd into the rows it reaches and then scaled by the diagonal, so row i ends as
  * d_i*x_i (one rounded product; x_i itself if unit) followed by fma(x_j, T[i,j], .) over j = i+1, i+2, ... ('U') or
  * j = i-1, i-2, ... ('L') with the ORIGINAL x_j. */
 int oracle_dtbmv(char uplo, char trans, char diag, i64 n, i64 k, const double *a, i64 lda, double *x)
 {
     const int up = (uplo == 'U' || uplo == 'u'), unit = (diag == 'U' || diag == 'u');
+    const int tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
     if (!up && !(uplo == 'L' || uplo == 'l')) return -1;
-    if (!(trans == 'N' || trans == 'n')) return -2;
+    if (!tr && !(trans == 'N' || trans == 'n')) return -2;
     if (!unit && !(diag == 'N' || diag == 'n')) return -3;
     if (n < 0) return -4;
     if (k < 0) return -5;
@@ -319,7 +341,12 @@ int oracle_dtbmv(char uplo, char trans, char diag, i64 n, i64 k, const double *a
     if (!y) return -100;
     for (i64 i = 0; i < n; ++i) {
         double acc;
-        if (up) {
+        if (tr) { /* (T^T x)_i = d_i x_i + sum over column i of T (dot; tolerance, see oracle_dtbsv) */
+            double dot = 0.0;
+            if (up) for (i64 r = imax(0, i - k); r < i; ++r) dot = fma(a[(k + r - i) + i * lda], x[r], dot);
+            else for (i64 r = i + 1; r <= imin(n - 1, i + k); ++r) dot = fma(a[(r - i) + i * lda], x[r], dot);
+            acc = (unit ? x[i] : x[i] * a[(up ? k : 0) + i * lda]) + dot;
+        } else if (up) {
             acc = unit ? x[i] : x[i] * a[k + i * lda];
             for (i64 j = i + 1; j <= imin(n - 1, i + k); ++j) acc = fma(x[j], a[(k + i - j) + j * lda], acc);
         } else {

@@ -38,6 +38,25 @@ def test_tbsv_tbmv_bit_identical(bm, oracle_c, rng, shape):
             assert np.array_equal(x.cpu().numpy(), ref), (name, uplo, diag, n, k, extra)
 
 
+@pytest.mark.parametrize("shape", [(1, 0), (5, 2), (40, 3), (1000, 16), (4097, 40), (30000, 7), (3000, 300), (50, 80), (2500, 1024)])
+def test_tbsv_tbmv_transposed(bm, oracle_c, rng, shape):
+    """trans = 'T' (row-major layouts, src/tribanded.jl:86-96): dot-product forms; OpenBLAS' own summation order is
+    unspecified there, so the comparison with the oracle is to 1e-13 (relative to max|x|), like the other 'T' paths."""
+    n, k = shape
+    for uplo, diag, extra in itertools.product("UL", "NU", (0, 3)):
+        a = _tri_band(rng, n, k, uplo, extra)
+        lda = a.shape[0]
+        dA = _dev(a)
+        for name, fn in (("tbsv", bm.tbsv_), ("tbmv", bm.tbmv_)):
+            x0 = rng.standard_normal(n)
+            ref = x0.copy()
+            assert getattr(oracle_c, name)(uplo, "T", diag, n, k, a, lda, ref) == 0
+            x = torch.as_tensor(x0).cuda()
+            fn(uplo, "T", diag, n, k, dA, x)
+            got = x.cpu().numpy()
+            assert np.max(np.abs(got - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref))), (name, uplo, diag, n, k, extra)
+
+
 def test_triangular_views_of_a_banded_matrix(bm, oracle_c, rng):
     """ldiv!(UpperTriangular(A), x) etc.: the triangular views share A's data array (rows 1:u+1 / u+1:u+l+1,
     src/tribanded.jl:47-84), lda = l+u+1."""
@@ -68,6 +87,6 @@ def test_tb_argument_errors(bm, rng):
         bm.tbmv_("U", "N", "N", n, k, dA, x[:-1])
     with pytest.raises(ValueError):
         bm.tbsv_("U", "N", "N", n, k + 1, dA, x)
-    with pytest.raises(bm.BMB200Error):  # trans = 'T' (row-major layouts in the reference) is not built
-        bm.tbsv_("U", "T", "N", n, k, dA, x)
+    with pytest.raises(bm.BMB200Error):  # invalid trans
+        bm.tbsv_("U", "X", "N", n, k, dA, x)
     assert bm.tbsv_("L", "N", "U", 0, 0, torch.zeros((0, 1), dtype=torch.float64, device="cuda"), x[:0]).numel() == 0

@@ -205,3 +205,18 @@ def test_c_tbsv_tbmv_match_openblas_bit_for_bit(oracle_c, oracle_ob, rng, shape)
             if n <= 300:
                 ref = np.linalg.solve(T, x0) if name == "tbsv" else T @ x0
                 assert np.allclose(x1, ref, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape", [(5, 2), (100, 16), (257, 40), (3000, 7), (2000, 300), (50, 80)])
+def test_c_tbsv_tbmv_transposed_match_openblas(oracle_c, oracle_ob, rng, shape):
+    """'T': OpenBLAS uses its SIMD dot kernel (order unspecified) -> 1e-13, plus dense arithmetic."""
+    n, k = shape
+    for uplo, diag in itertools.product("UL", "NU"):
+        a = _tri_band(rng, n, k, uplo, 1)
+        lda = a.shape[0]
+        for name in ("tbsv", "tbmv"):
+            x0 = rng.standard_normal(n)
+            x1, x2 = x0.copy(), x0.copy()
+            assert getattr(oracle_c, name)(uplo, "T", diag, n, k, a, lda, x1) == 0
+            getattr(oracle_ob, name)(uplo, "T", diag, n, k, a, lda, x2)
+            assert np.max(np.abs(x1 - x2)) <= 1e-13 * max(1.0, np.max(np.abs(x2))), (name, uplo, diag)

@@ -2,6 +2,4 @@
 mkdir -p gpurun_out
 exec > gpurun_out/tb.log 2>&1
 set -x
-timeout 900 python -m pytest tests/test_gpu_tb.py -m gpu -x -q 2>&1 | tail -5
-timeout 300 python tools/time_tb.py 1048576 1024
-timeout 300 python tools/time_tb.py 4194304 64
+timeout 900 python -m pytest tests/test_gpu_tb.py -m gpu -x -q 2>&1 | tail -8
