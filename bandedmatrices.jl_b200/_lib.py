@@ -34,6 +34,7 @@ PROTOTYPES = {
     "bmb200_dgbtrs": (C.c_int, [vp, ch, i64, i64, i64, i64, vp, i64, vp, vp, i64]),
     "bmb200_dtbsv": (C.c_int, [vp, ch, ch, ch, i64, i64, vp, i64, vp, i64]),
     "bmb200_dtbmv": (C.c_int, [vp, ch, ch, ch, i64, i64, vp, i64, vp, i64]),
+    "bmb200_dsbmv": (C.c_int, [vp, ch, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
     "bmb200_dgbmv_host": (C.c_int, [vp, ch, i64, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
     "bmb200_dgbsv_host": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, vp, i64, C.POINTER(C.c_int)]),
     "bmb200_dgbmm_bb_host": (C.c_int, [vp] + [i64] * 9 + [dbl, vp, i64, vp, i64, dbl, vp, i64]),

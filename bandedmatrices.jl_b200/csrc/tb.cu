@@ -184,6 +184,120 @@ tbsv_t_chain(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 l
     }
 }
 
+// ---- symmetric band matvec: y <- alpha*S*x + beta*y, S symmetric with only its 'U' or 'L' triangle stored in triangular-band
+// storage (sbmv!, src/blas.jl:36-66; mul! of Symmetric{<:BandedMatrix}, src/symbanded/symbanded.jl:72-93).  SURVEY 8(f) rank 3.
+// Row i needs the stored triangle twice: S[i,j] on the stored side of the diagonal is a strided walk through OTHER columns
+// (coalesced over the 32 rows of a warp, exactly the tbmv sweep), and on the other side it is the lane's OWN column, contiguous
+// per lane.  OpenBLAS' dsbmv mixes an axpy and a SIMD dot per column (summation order unspecified): compared at 1e-13. ----
+template <bool UP>
+__global__ void __launch_bounds__(256)
+sbmv_sweep(i64 n, int k, double alpha, const double *__restrict__ a, i64 lda, const double *__restrict__ x, double beta, double *__restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const i64 st = lda - 1;
+    for (i64 rb = warp * 32; rb < n; rb += nwarps * 32) {
+        const i64 i = rb + lane;
+        const bool live = i < n;
+        if (alpha == 0.0) {  // DSBMV returns after the beta scaling: A and x are not read
+            if (live) y[i] = (beta == 0.0) ? 0.0 : __dmul_rn(beta, y[i]);
+            continue;
+        }
+        // (1) own column: diagonal + the k entries on the stored side, contiguous: 'U' rows i-k..i-1 above, 'L' rows i+1..i+k below
+        double acc = 0.0;
+        if (live) {
+            const double *col = a + i * lda + (UP ? k : 0);  // diagonal entry; S[i-d, i] = col[-d] ('U'), S[i+d, i] = col[+d] ('L')
+            const i64 dmax = UP ? ((i < k) ? i : k) : ((n - 1 - i < k) ? n - 1 - i : k);
+            const double *xp = x + i;
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;  // four chains: a 1024-term dependent FMA chain would be latency bound
+            i64 d = 1;
+#pragma unroll 2
+            for (; d + 3 <= dmax; d += 4) {
+                c0 = fma(UP ? col[-d] : col[d], UP ? xp[-d] : xp[d], c0);
+                c1 = fma(UP ? col[-d - 1] : col[d + 1], UP ? xp[-d - 1] : xp[d + 1], c1);
+                c2 = fma(UP ? col[-d - 2] : col[d + 2], UP ? xp[-d - 2] : xp[d + 2], c2);
+                c3 = fma(UP ? col[-d - 3] : col[d + 3], UP ? xp[-d - 3] : xp[d + 3], c3);
+            }
+            for (; d <= dmax; ++d) c0 = fma(UP ? col[-d] : col[d], UP ? xp[-d] : xp[d], c0);
+            acc = fma(col[0], xp[0], (c0 + c1) + (c2 + c3));
+        }
+        // (2) the other side of the diagonal: S[i,j] = stored entry (row i, column j), j > i ('U') or j < i ('L'): column sweep
+        const double *p = a + (UP ? k : 0) + i;  // stored T[i,j] = p[j*(lda-1)]
+        const i64 jlo = UP ? rb + 1 : ((rb - k > 0) ? rb - k : 0);
+        const i64 jhi = UP ? ((rb + 31 + k < n - 1) ? rb + 31 + k : n - 1) : rb + 30;
+        const bool all = rb + 31 < n;
+        const i64 lo_all = all ? (UP ? rb + 32 : ((rb + 31 - k > 0) ? rb + 31 - k : 0)) : 1;
+        const i64 hi_all = all ? (UP ? ((rb + k < n - 1) ? rb + k : n - 1) : rb - 1) : 0;
+        if (jlo <= jhi) {
+            const i64 nch = (jhi - jlo) / 8 + 1;
+            double va[8], xa[8], vb[8], xb[8];
+            bool fa, fb = false;
+            i64 j0 = UP ? jlo : jhi;
+            fa = tbmv_load8<UP>(p, st, x, j0, lo_all, hi_all, jlo, jhi, i, k, live, va, xa);
+            for (i64 c = 0; c < nch; c += 2) {
+                const i64 j1 = UP ? j0 + 8 : j0 - 8;
+                if (c + 1 < nch) fb = tbmv_load8<UP>(p, st, x, j1, lo_all, hi_all, jlo, jhi, i, k, live, vb, xb);
+                acc = tbmv_fma8<UP>(acc, fa, j0, jlo, jhi, i, k, live, va, xa);
+                const i64 j2 = UP ? j1 + 8 : j1 - 8;
+                if (c + 2 < nch) fa = tbmv_load8<UP>(p, st, x, j2, lo_all, hi_all, jlo, jhi, i, k, live, va, xa);
+                if (c + 1 < nch) acc = tbmv_fma8<UP>(acc, fb, j1, jlo, jhi, i, k, live, vb, xb);
+                j0 = j2;
+            }
+        }
+        if (live) y[i] = (beta == 0.0) ? __dmul_rn(alpha, acc) : fma(alpha, acc, __dmul_rn(beta, y[i]));
+    }
+}
+
+// narrow bands: one thread per row; both uses of a stored entry fall into the same or the neighbouring thread's cache lines
+template <bool UP>
+__global__ void __launch_bounds__(256)
+sbmv_rows(i64 n, int k, double alpha, const double *__restrict__ a, i64 lda, const double *__restrict__ x, double beta, double *__restrict__ y)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        if (alpha == 0.0) {
+            y[i] = (beta == 0.0) ? 0.0 : __dmul_rn(beta, y[i]);
+            continue;
+        }
+        const double *col = a + i * lda + (UP ? k : 0);  // diagonal of the own column
+        double acc = col[0] * x[i];
+        for (int d = 1; d <= k; ++d) {
+            const i64 js = UP ? i - d : i + d;  // stored side: own column, entry col[-d] / col[+d]
+            const i64 jo = UP ? i + d : i - d;  // other side: entry (row i) of column jo
+            if (js >= 0 && js < n) acc = fma(UP ? col[-d] : col[d], x[js], acc);
+            if (jo >= 0 && jo < n) acc = fma(a[(UP ? k - d : d) + jo * lda], x[jo], acc);
+        }
+        y[i] = (beta == 0.0) ? __dmul_rn(alpha, acc) : fma(alpha, acc, __dmul_rn(beta, y[i]));
+    }
+}
+
+extern "C" int bmb200_dsbmv(bmb200_handle_t h, char uplo, int64_t n, int64_t k, double alpha, const double *dA, int64_t lda, const double *dx,
+                            int64_t incx, double beta, double *dy, int64_t incy)
+{
+    if (!h) return -1;
+    const int up = (uplo == 'U' || uplo == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -2;
+    if (n < 0) return -3;
+    if (k < 0 || k >= ((int64_t)1 << 30)) return -4;
+    if (lda < k + 1) return -7;
+    if (incx != 1) return -9;
+    if (incy != 1) return -12;
+    if (n == 0) return 0;
+    if (!dA || !dx || !dy) return -6;
+    if (dx == dy) return -8;  // the reference un-aliases x and y before the call (symbanded.jl:77-83)
+    DeviceGuard g(h->device);
+    if (k < 16) {
+        const i64 blocks = imin64(cdiv64(n, 256), (i64)h->sm_count * 16);
+        if (up) sbmv_rows<true><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, alpha, dA, lda, dx, beta, dy);
+        else sbmv_rows<false><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, alpha, dA, lda, dx, beta, dy);
+    } else {
+        const i64 blocks = imin64(cdiv64(n, 32 * 8), (i64)h->sm_count * 8);
+        if (up) sbmv_sweep<true><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, alpha, dA, lda, dx, beta, dy);
+        else sbmv_sweep<false><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, alpha, dA, lda, dx, beta, dy);
+    }
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
 static int tb_check(char uplo, char trans, char diag, int64_t n, int64_t k, int64_t lda, int64_t incx, int &up, int &unit)
 {
     up = (uplo == 'U' || uplo == 'u');

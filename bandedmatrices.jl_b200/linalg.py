@@ -532,6 +532,45 @@ def lmul_tri_(uplo: str, unit: bool, A: BandedMatrix, x: torch.Tensor) -> torch.
     return tbmv_(uplo, "N", "U" if unit else "N", A.m, k, d, x)
 
 
+# ---------------------------------------------------------------------------------------------------
+# Symmetric band matvec: sbmv! (src/blas.jl:36-66) and mul! of Symmetric{<:BandedMatrix} (src/symbanded/symbanded.jl:72-93)
+# ---------------------------------------------------------------------------------------------------
+def sbmv_(uplo: str, k: int, alpha, Adata: torch.Tensor, x: torch.Tensor, beta, y: torch.Tensor) -> torch.Tensor:
+    """``sbmv!(uplo, k, alpha, A, x, beta, y)`` (src/blas.jl:64-66); ``Adata`` is the (n, rows >= k+1) band array of the stored
+    triangle (a row-range view of ``BandedMatrix.data``)."""
+    n = Adata.shape[0]
+    if x.shape[0] != n or y.shape[0] != n:
+        raise DimensionMismatch("*")
+    if Adata.shape[1] < k + 1:
+        raise ValueError("symmetric banded data missing")
+    if x.dim() != 1 or y.dim() != 1 or _inc(x) != 1 or _inc(y) != 1:
+        raise TypeError("x and y must be contiguous vectors")
+    if n == 0:
+        return y
+    hd = _h(y)
+    lda = max(1, Adata.stride(0)) if n > 1 else max(1, Adata.shape[1])
+    rc = hd.lib.bmb200_dsbmv(hd.h, uplo.encode(), n, k, float(alpha), vp(Adata.data_ptr()), lda, vp(x.data_ptr()), 1, float(beta),
+                             vp(y.data_ptr()), 1)
+    hd.check(rc, "dsbmv")
+    return y
+
+
+def mul_sym_(y: torch.Tensor, uplo: str, A: BandedMatrix, x: torch.Tensor, alpha=1.0, beta=0.0) -> torch.Tensor:
+    """``mul!(y, Symmetric(A, uplo), x, alpha, beta)`` (symbanded.jl:84-93): only A's `uplo` triangle is read."""
+    if A.m != A.n:
+        raise DimensionMismatch("matrix is not square")
+    if y.shape[0] != A.m or x.shape[0] != A.n:
+        raise DimensionMismatch("*")
+    k = A.u if uplo == "U" else A.l  # bandwidth(Symmetric(A, uplo))
+    if k < 0:
+        _fill_vec(y, beta)
+        return y
+    if x.data_ptr() == y.data_ptr():  # _banded_sbmv!: x === y -> copy(x)
+        x = x.clone()
+    d, _ = _tri_data(uplo, A)
+    return sbmv_(uplo, k, alpha, d, x, beta, y)
+
+
 def factorize(A: BandedMatrix):
     """_factorize (linalg.jl:75): square -> lu; rectangular -> qr (out of scope here)."""
     if A.m != A.n:

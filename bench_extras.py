@@ -121,6 +121,17 @@ def cpu_extras(L, cores):
     tf, ts = lu_solve(ns, 1024, 1024, 1, dominant=True)
     out["C5"] = {"sample": "n=2^14 of 2^20 columns, l=u=1024, diagonally dominant, 1 RHS", "lu_sample_ms": round(tf, 1), "solve_sample_ms": round(ts, 1),
                  "lu_full_ms_extrapolated": round(tf * full / ns, 1), "solve_full_ms_extrapolated": round(ts * full / ns, 1)}
+    # symmetric band: dsbmv_ 'U', k=3 on n=2^24 of 2^27 rows (1 thread), linear in n
+    ns, full = 1 << 24, 1 << 27
+    a = np.asfortranarray(rng.random((4, ns)))
+    xv, yv = rng.random(ns), np.zeros(ns)
+    L.drv_sbmv.restype = dbl
+    L.drv_sbmv.argtypes = [C.c_char, i64, i64, dbl, vp, i64, vp, dbl, vp]
+    L.drv_set_threads(1)
+    t_sb = min(L.drv_sbmv(b"U", ns, 3, 1.0, a.ctypes.data, 4, xv.ctypes.data, 0.0, yv.ctypes.data) for _ in range(3))
+    out["SB"] = {"sample": "n=2^24 of 2^27 rows, k=3, 1 thread", "sbmv_sample_ms": round(1e3 * t_sb, 1), "sbmv_full_ms_extrapolated": round(1e3 * t_sb * full / ns, 1),
+                 "GBs": round(8.0 * ns * 6 / t_sb / 1e9, 2)}
+    del a, xv, yv
     # triangular band: dtbsv_/dtbmv_ 'U','N','N', k=1024 on n=2^16 of 2^20 columns (1 thread: OpenBLAS' level-2 band
     # kernels are not threaded at these sizes), linear in n
     ns, full, k = 1 << 16, 1 << 20, 1024
@@ -200,6 +211,14 @@ def run_extras(bm, c3_n=1 << 22, c4_n=1 << 20, c4_rhs=256):
     t_sv = _time(lambda: bm.ldiv_tri_("U", False, A, x), reps=2, setup=lambda: x.copy_(b))
     t_mv = _time(lambda: bm.lmul_tri_("U", False, A, x), reps=2, setup=lambda: x.copy_(b))
     by = 8.0 * n * (N + 1) + 16.0 * n
+    # ---- symmetric band matvec: the C2 shape with only the upper triangle stored ----
+    ns, ks = 1 << 27, 3
+    Sd = torch.rand((ns, ks + 1), dtype=torch.float64, device="cuda")
+    xs, ys = torch.rand(ns, dtype=torch.float64, device="cuda"), torch.empty(ns, dtype=torch.float64, device="cuda")
+    t_sb = _time(lambda: bm.sbmv_("U", ks, 1.0, Sd, xs, 0.0, ys), reps=5)
+    by_sb = 8.0 * ns * (ks + 1 + 2)
+    out["SB"] = {"n": ns, "k": ks, "sbmv_U_ms": round(t_sb, 3), "GBs": round(by_sb / t_sb / 1e6, 1), "algorithmic_bytes": by_sb}
+    del Sd, xs, ys
     out["TB"] = {"n": n, "k": N, "tbsv_U_ms": round(t_sv, 2), "tbmv_U_ms": round(t_mv, 3), "tbmv_GBs": round(by / t_mv / 1e6, 1),
                  "algorithmic_bytes": by}
     return out

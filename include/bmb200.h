@@ -120,6 +120,14 @@ int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n,
 int bmb200_dtbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k,
                  const double *dA, int64_t lda, double *dx, int64_t incx);
 
+/* ---- symmetric band matvec ----------------------------------------------
+ * Replaces dsbmv_ reached through sbmv!(uplo, n, k, alpha, A, lda, x, incx, beta, y, incy) (src/blas.jl:36-66), i.e. mul! of
+ * Symmetric{<:BandedMatrix} (src/symbanded/symbanded.jl:72-93).  Only the `uplo` triangle is stored, in triangular-band
+ * storage as for dtbsv.  y <- alpha*S*x + beta*y (beta == 0 overwrites); incx = incy = 1; x must not alias y.  Equal to
+ * OpenBLAS dsbmv_ to 1e-13 (its summation order is unspecified).                                         */
+int bmb200_dsbmv(bmb200_handle_t h, char uplo, int64_t n, int64_t k, double alpha, const double *dA,
+                 int64_t lda, const double *dx, int64_t incx, double beta, double *dy, int64_t incy);
+
 /* ---- host-buffer forms: what a Fortran-ABI caller with HOST arrays gets (bench.py "e2e") ----
  * Same semantics as the calls above; inputs are copied host->device in pipelined chunks, the
  * result is copied back, and the call returns after the result is in host memory.           */

@@ -138,4 +138,12 @@ for (jl, sym) in ((:tbsv!, :bmb200_dtbsv), (:tbmv!, :bmb200_dtbmv))
     end
 end
 
+# ---- symmetric band matvec: shadows banded_sbmv! (src/symbanded/symbanded.jl:72-73) for device-resident data ----
+function BandedMatrices.banded_sbmv!(uplo, α::Float64, A::Symmetric{Float64,<:DBanded}, x::DVec, β::Float64, y::DVec)
+    D = BandedMatrices.symbandeddata(A)   # row-range view of the parent's device data array
+    chk(ccall((:bmb200_dsbmv, libbmb200), Cint, (Handle, UInt8, Int64, Int64, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Int64),
+              handle(), uplo, size(D, 2), BandedMatrices.bandwidth(A), α, pointer(D), max(1, stride(D, 2)), pointer(x), stride(x, 1), β, pointer(y), stride(y, 1)), "dsbmv")
+    y
+end
+
 end # module

@@ -82,7 +82,12 @@ class _CBackend:
         for f in (L.oracle_dtbsv, L.oracle_dtbmv):
             f.restype = C.c_int
             f.argtypes = [C.c_char, C.c_char, C.c_char, i64, i64, C.c_void_p, i64, C.c_void_p]
+        L.oracle_dsbmv.restype = C.c_int
+        L.oracle_dsbmv.argtypes = [C.c_char, i64, i64, C.c_double, C.c_void_p, i64, C.c_void_p, C.c_double, C.c_void_p]
         self.L = L
+
+    def sbmv(self, uplo, n, k, alpha, a, lda, x, beta, y):
+        return self.L.oracle_dsbmv(uplo.encode(), n, k, alpha, _ptr(a), lda, _ptr(x), beta, _ptr(y))
 
     def tbsv(self, uplo, trans, diag, n, k, a, lda, x):
         return self.L.oracle_dtbsv(uplo.encode(), trans.encode(), diag.encode(), n, k, _ptr(a), lda, _ptr(x))
@@ -134,6 +139,12 @@ class _OpenBLASBackend:
         r = C.byref
         fn(C.c_char_p(uplo.encode()), C.c_char_p(trans.encode()), C.c_char_p(diag.encode()), r(i64(n)), r(i64(k)), _ptr(a),
            r(i64(lda)), _ptr(x), r(i64(1)), C.c_long(1), C.c_long(1), C.c_long(1))
+        return 0
+
+    def sbmv(self, uplo, n, k, alpha, a, lda, x, beta, y):  # dsbmv_ as src/blas.jl:51-60 calls it
+        r = C.byref
+        self.L.scipy_dsbmv_64_(C.c_char_p(uplo.encode()), r(i64(n)), r(i64(k)), r(C.c_double(alpha)), _ptr(a), r(i64(lda)), _ptr(x),
+                               r(i64(1)), r(C.c_double(beta)), _ptr(y), r(i64(1)), C.c_long(1))
         return 0
 
     def tbsv(self, uplo, trans, diag, n, k, a, lda, x):  # dtbsv_ as src/blas.jl:132-137 calls it

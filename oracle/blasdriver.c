@@ -26,6 +26,8 @@ typedef void (*gbtrs_t)(const char *, const i64 *, const i64 *, const i64 *, con
                         const i64 *, const i64 *, double *, const i64 *, i64 *, long);
 typedef void (*tb_t)(const char *, const char *, const char *, const i64 *, const i64 *, const double *, const i64 *, double *,
                      const i64 *, long, long, long);
+typedef void (*sbmv_t)(const char *, const i64 *, const i64 *, const double *, const double *, const i64 *, const double *, const i64 *,
+                       const double *, double *, const i64 *, long);
 typedef void (*setthr_t)(int);
 
 static void *lib;
@@ -34,6 +36,7 @@ static gbtrf_t f_gbtrf;
 static gbtrs_t f_gbtrs;
 static setthr_t f_setthr;
 static tb_t f_tbsv, f_tbmv;
+static sbmv_t f_sbmv;
 
 static double now(void)
 {
@@ -53,7 +56,8 @@ int drv_open(const char *path)
     f_setthr = (setthr_t)dlsym(lib, "scipy_openblas_set_num_threads64_");
     f_tbsv = (tb_t)dlsym(lib, "scipy_dtbsv_64_");
     f_tbmv = (tb_t)dlsym(lib, "scipy_dtbmv_64_");
-    return (f_gbmv && f_gbtrf && f_gbtrs && f_setthr && f_tbsv && f_tbmv) ? 0 : -2;
+    f_sbmv = (sbmv_t)dlsym(lib, "scipy_dsbmv_64_");
+    return (f_gbmv && f_gbtrf && f_gbtrs && f_setthr && f_tbsv && f_tbmv && f_sbmv) ? 0 : -2;
 }
 
 void drv_set_threads(int k) { f_setthr(k); }
@@ -114,5 +118,14 @@ double drv_tb(int which, char uplo, char diag, i64 n, i64 k, const double *a, i6
     const i64 one = 1;
     double t0 = now();
     (which ? f_tbmv : f_tbsv)(&uplo, "N", &diag, &n, &k, a, &lda, x, &one, 1, 1, 1);
+    return now() - t0;
+}
+
+/* dsbmv_ as sbmv! calls it (src/blas.jl:51-60) */
+double drv_sbmv(char uplo, i64 n, i64 k, double alpha, const double *a, i64 lda, const double *x, double beta, double *y)
+{
+    const i64 one = 1;
+    double t0 = now();
+    f_sbmv(&uplo, &n, &k, &alpha, a, &lda, x, &one, &beta, y, &one, 1);
     return now() - t0;
 }

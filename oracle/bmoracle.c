@@ -360,6 +360,39 @@ int oracle_dtbmv(char uplo, char trans, char diag, i64 n, i64 k, const double *a
     return 0;
 }
 
+/* y <- alpha*S*x + beta*y, S symmetric, `uplo` triangle in triangular-band storage (sbmv!, src/blas.jl:36-66; mul! of
+ * Symmetric{<:BandedMatrix}, src/symbanded/symbanded.jl:72-93).  Reference-BLAS DSBMV loop order; OpenBLAS pairs an axpy with a
+ * SIMD dot per column (order unspecified), so the pin is to tolerance. */
+int oracle_dsbmv(char uplo, i64 n, i64 k, double alpha, const double *a, i64 lda, const double *x, double beta, double *y)
+{
+    const int up = (uplo == 'U' || uplo == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -1;
+    if (n < 0) return -2;
+    if (k < 0) return -3;
+    if (lda < k + 1) return -6;
+    for (i64 i = 0; i < n; ++i) y[i] = (beta == 0.0) ? 0.0 : beta * y[i];
+    if (alpha == 0.0) return 0;
+    for (i64 j = 0; j < n; ++j) {
+        const double t1 = alpha * x[j];
+        double t2 = 0.0;
+        if (up) {
+            for (i64 i = imax(0, j - k); i < j; ++i) {
+                y[i] = fma(t1, a[(k + i - j) + j * lda], y[i]);
+                t2 = fma(a[(k + i - j) + j * lda], x[i], t2);
+            }
+            y[j] = y[j] + t1 * a[k + j * lda] + alpha * t2;
+        } else {
+            y[j] = y[j] + t1 * a[j * lda];
+            for (i64 i = j + 1; i <= imin(n - 1, j + k); ++i) {
+                y[i] = fma(t1, a[(i - j) + j * lda], y[i]);
+                t2 = fma(a[(i - j) + j * lda], x[i], t2);
+            }
+            y[j] = y[j] + alpha * t2;
+        }
+    }
+    return 0;
+}
+
 /* banded_mul! triple loop (src/generic/matmul.jl:143-172): the semantic definition of
  * banded x banded used as a second, independent check of oracle_gbmm.  C gets zeros in bands
  * beyond (Al+Bl, Au+Bu).  Band widths may exceed the matrix size; all must be >= 0 here. */

@@ -77,6 +77,47 @@ def test_triangular_views_of_a_banded_matrix(bm, oracle_c, rng):
             assert np.array_equal(x.cpu().numpy(), ref), (name, uplo, unit)
 
 
+@pytest.mark.parametrize("shape", [(1, 0), (5, 2), (40, 3), (1000, 16), (4097, 40), (100000, 4), (6000, 300), (50, 80), (20011, 1024)])
+def test_sbmv_matches_oracle(bm, oracle_c, rng, shape):
+    """sbmv! (src/blas.jl:36-66) / mul!(y, Symmetric(A), x) (symbanded.jl:72-93): OpenBLAS' summation order is unspecified
+    (axpy + SIMD dot per column), so 1e-13 relative to max|y|; beta == 0 overwrites NaN; alpha == 0 does not read A."""
+    n, k = shape
+    for uplo, (al, be), extra in itertools.product("UL", [(1.0, 0.0), (0.7, -1.3), (0.0, 2.0)], (0, 3)):
+        a = np.asfortranarray(rng.standard_normal((k + 1 + extra, n)))
+        lda = a.shape[0]
+        if al == 0.0:
+            a[:] = np.nan
+        x0 = rng.standard_normal(n)
+        y0 = rng.standard_normal(n)
+        if be == 0.0:
+            y0[:] = np.nan
+        ref = y0.copy()
+        assert oracle_c.sbmv(uplo, n, k, al, a, lda, x0, be, ref) == 0
+        y = torch.as_tensor(y0).cuda()
+        bm.sbmv_(uplo, k, al, _dev(a), torch.as_tensor(x0).cuda(), be, y)
+        got = y.cpu().numpy()
+        assert np.isfinite(got).all()
+        assert np.max(np.abs(got - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref))), (uplo, al, be, n, k)
+
+
+def test_mul_symmetric_view(bm, rng):
+    """mul!(y, Symmetric(A, uplo), x): reads only the `uplo` triangle of A's data; x === y is un-aliased first."""
+    n, l, u = 3000, 9, 14
+    data = np.asfortranarray(rng.standard_normal((l + u + 1, n)))
+    A = bm.BandedMatrix.from_banddata(data, n, l, u)
+    D = A.to_dense()
+    for uplo in "UL":
+        T = np.triu(D) if uplo == "U" else np.tril(D)
+        S = T + T.T - np.diag(np.diag(D))
+        x0 = rng.standard_normal(n)
+        y = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+        bm.mul_sym_(y, uplo, A, torch.as_tensor(x0).cuda())
+        assert np.allclose(y.cpu().numpy(), S @ x0, rtol=1e-12, atol=1e-12)
+        z = torch.as_tensor(x0).cuda()
+        bm.mul_sym_(z, uplo, A, z, 2.0, 0.0)  # aliased
+        assert np.allclose(z.cpu().numpy(), 2.0 * (S @ x0), rtol=1e-12, atol=1e-12)
+
+
 def test_tb_argument_errors(bm, rng):
     n, k = 10, 2
     dA = _dev(_tri_band(rng, n, k, "U"))

@@ -25,3 +25,16 @@ for uplo in "UL":
             ts.append(e0.elapsed_time(e1))
         ms = min(ts[1:])
         print(f"{name} {uplo} n={n} k={k}: {ms:.3f} ms  {8.0*n*(k+1)/ms/1e6:.0f} GB/s")
+for uplo in "UL":
+    xx = torch.rand(n, dtype=torch.float64, device="cuda")
+    yy = torch.zeros(n, dtype=torch.float64, device="cuda")
+    ts = []
+    for r in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        bm.sbmv_(uplo, k, 1.0, d, xx, 0.0, yy)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = min(ts[1:])
+    print(f"sbmv {uplo} n={n} k={k}: {ms:.3f} ms  {8.0*n*(k+3)/ms/1e6:.0f} GB/s algorithmic (stored triangle + x + y once)")
