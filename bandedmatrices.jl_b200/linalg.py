@@ -571,6 +571,48 @@ def mul_sym_(y: torch.Tensor, uplo: str, A: BandedMatrix, x: torch.Tensor, alpha
     return sbmv_(uplo, k, alpha, d, x, beta, y)
 
 
+# ---------------------------------------------------------------------------------------------------
+# Band-aligned elementwise operations between different bandwidths (the steps either side of the hot path):
+# banded_axpy! (src/banded/BandedMatrix.jl:1006-1015, src/generic/broadcast.jl:978-1020) and copyto! (broadcast.jl:175-230)
+# ---------------------------------------------------------------------------------------------------
+def _ld_band(A: BandedMatrix) -> int:
+    return max(1, A.data.stride(0)) if A.n > 1 else max(1, A.data.shape[1])
+
+
+def axpy_(a, X: BandedMatrix, Y: BandedMatrix) -> BandedMatrix:
+    """``axpy!(a, X, Y)``: Y += a*X.  Equal bandwidths: one FMA per slot of the data arrays (``axpy!(a, X.data, Y.data)``);
+    otherwise ``a*X[k,j] + Y[k,j]`` on the overlapping bands, ``BandError`` if X has a non-zero entry outside Y's bands."""
+    if X.shape != Y.shape:
+        raise DimensionMismatch(f"X has size {X.shape} but Y has size {Y.shape}")
+    if X.m == 0 or X.n == 0:
+        return Y
+    hd = _h(Y.data)
+    out = C.c_int64(0)
+    rc = hd.lib.bmb200_dband_axpy(hd.h, X.m, X.n, float(a), X.l, X.u, vp(X.data.data_ptr()), _ld_band(X), Y.l, Y.u,
+                                  vp(Y.data.data_ptr()), _ld_band(Y), C.byref(out))
+    hd.check(rc, "dband_axpy")
+    if out.value:
+        raise BandError(Y, (X.l if X.l > Y.l else -X.u))
+    return Y
+
+
+def copyto_(dest: BandedMatrix, src: BandedMatrix) -> BandedMatrix:
+    """``copyto!(dest, src)`` between bandwidths: overlapping bands copied, dest's other bands zeroed, ``BandError`` if src has
+    a non-zero entry outside dest's bands."""
+    if dest.shape != src.shape:
+        raise DimensionMismatch(f"dest has size {dest.shape} but src has size {src.shape}")
+    if dest.m == 0 or dest.n == 0:
+        return dest
+    hd = _h(dest.data)
+    out = C.c_int64(0)
+    rc = hd.lib.bmb200_dband_copy(hd.h, src.m, src.n, src.l, src.u, vp(src.data.data_ptr()), _ld_band(src), dest.l, dest.u,
+                                  vp(dest.data.data_ptr()), _ld_band(dest), C.byref(out))
+    hd.check(rc, "dband_copy")
+    if out.value:
+        raise BandError(dest, (src.l if src.l > dest.l else -src.u))
+    return dest
+
+
 def factorize(A: BandedMatrix):
     """_factorize (linalg.jl:75): square -> lu; rectangular -> qr (out of scope here)."""
     if A.m != A.n:

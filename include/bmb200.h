@@ -128,6 +128,18 @@ int bmb200_dtbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n,
 int bmb200_dsbmv(bmb200_handle_t h, char uplo, int64_t n, int64_t k, double alpha, const double *dA,
                  int64_t lda, const double *dx, int64_t incx, double beta, double *dy, int64_t incy);
 
+/* ---- band-aligned elementwise operations between different bandwidths ----
+ * bmb200_dband_axpy replaces banded_axpy!(a, X, Y) (src/banded/BandedMatrix.jl:1006-1015 -> axpy!(a, X.data, Y.data) for equal
+ * bandwidths: one FMA per slot, as OpenBLAS daxpy; src/generic/broadcast.jl:978-1020 otherwise: Y[k,j] = a*X[k,j] + Y[k,j] on
+ * the overlapping bands).  bmb200_dband_copy replaces copyto!(dest, src) between bandwidths (broadcast.jl:175-230): overlapping
+ * bands copied, dest's other in-matrix band entries zeroed.  *nonzero_outside (host) = number of non-zero entries of X / src in
+ * bands the destination does not store; if it is not 0 nothing was written and the caller raises BandError.  The calls that
+ * have to look (unequal bandwidths) synchronise.                                                          */
+int bmb200_dband_axpy(bmb200_handle_t h, int64_t m, int64_t n, double a, int64_t xl, int64_t xu, const double *dX,
+                      int64_t ldx, int64_t yl, int64_t yu, double *dY, int64_t ldy, int64_t *nonzero_outside);
+int bmb200_dband_copy(bmb200_handle_t h, int64_t m, int64_t n, int64_t sl, int64_t su, const double *dS, int64_t lds,
+                      int64_t dl, int64_t du, double *dD, int64_t ldd, int64_t *nonzero_outside);
+
 /* ---- host-buffer forms: what a Fortran-ABI caller with HOST arrays gets (bench.py "e2e") ----
  * Same semantics as the calls above; inputs are copied host->device in pipelined chunks, the
  * result is copied back, and the call returns after the result is in host memory.           */

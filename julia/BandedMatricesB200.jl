@@ -146,4 +146,25 @@ function BandedMatrices.banded_sbmv!(uplo, α::Float64, A::Symmetric{Float64,<:D
     y
 end
 
+# ---- band-aligned elementwise operations between different bandwidths: shadow banded_axpy! (src/banded/BandedMatrix.jl:1006-1015)
+# ---- and the identity broadcast copyto! (src/generic/broadcast.jl:175-230) for device-resident data ----
+function BandedMatrices.banded_axpy!(a::Number, X::DBanded, Y::DBanded)
+    size(X) == size(Y) || throw(DimensionMismatch("X has size \$(size(X)) but Y has size \$(size(Y))"))
+    (xl, xu), (yl, yu) = bandwidths(X), bandwidths(Y)
+    out = Ref{Int64}(0)
+    chk(ccall((:bmb200_dband_axpy, libbmb200), Cint, (Handle, Int64, Int64, Float64, Int64, Int64, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ref{Int64}),
+              handle(), size(X, 1), size(X, 2), Float64(a), xl, xu, X.data, stride(X.data, 2), yl, yu, Y.data, stride(Y.data, 2), out), "dband_axpy")
+    out[] == 0 || throw(BandError(Y, xl > yl ? xl : -xu))
+    Y
+end
+function BandedMatrices._banded_broadcast!(dest::DBanded, ::typeof(identity), src::DBanded, ::BandedMatrices.BandedColumns, ::BandedMatrices.BandedColumns)
+    size(dest) == size(src) || throw(DimensionMismatch())
+    (sl, su), (dl, du) = bandwidths(src), bandwidths(dest)
+    out = Ref{Int64}(0)
+    chk(ccall((:bmb200_dband_copy, libbmb200), Cint, (Handle, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ref{Int64}),
+              handle(), size(src, 1), size(src, 2), sl, su, src.data, stride(src.data, 2), dl, du, dest.data, stride(dest.data, 2), out), "dband_copy")
+    out[] == 0 || throw(BandError(dest, sl > dl ? sl : -su))
+    dest
+end
+
 end # module
