@@ -149,7 +149,7 @@ end
 # ---- band-aligned elementwise operations between different bandwidths: shadow banded_axpy! (src/banded/BandedMatrix.jl:1006-1015)
 # ---- and the identity broadcast copyto! (src/generic/broadcast.jl:175-230) for device-resident data ----
 function BandedMatrices.banded_axpy!(a::Number, X::DBanded, Y::DBanded)
-    size(X) == size(Y) || throw(DimensionMismatch("X has size \$(size(X)) but Y has size \$(size(Y))"))
+    size(X) == size(Y) || throw(DimensionMismatch("X has size $(size(X)) but Y has size $(size(Y))"))
     (xl, xu), (yl, yu) = bandwidths(X), bandwidths(Y)
     out = Ref{Int64}(0)
     chk(ccall((:bmb200_dband_axpy, libbmb200), Cint, (Handle, Int64, Int64, Float64, Int64, Int64, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ref{Int64}),
