@@ -219,6 +219,15 @@ def run_extras(bm, c3_n=1 << 22, c4_n=1 << 20, c4_rhs=256):
     by_sb = 8.0 * ns * (ks + 1 + 2)
     out["SB"] = {"n": ns, "k": ks, "sbmv_U_ms": round(t_sb, 3), "GBs": round(by_sb / t_sb / 1e6, 1), "algorithmic_bytes": by_sb}
     del Sd, xs, ys
+    # ---- band-aligned elementwise ops: Y += a*X on the C2 shape, equal and unequal bandwidths ----
+    ne = 1 << 26
+    Xe, Ye = bm.brand(ne, ne, 4, 3, seed=11), bm.brand(ne, ne, 4, 3, seed=12)
+    t_eq = _time(lambda: bm.axpy_(0.5, Xe, Ye), reps=5)
+    Yw = bm.brand(ne, ne, 5, 4, seed=13)
+    t_ne = _time(lambda: bm.axpy_(0.5, Xe, Yw), reps=3)
+    out["EW"] = {"n": ne, "axpy_equal_bands_ms": round(t_eq, 3), "axpy_equal_GBs": round(3 * 8.0 * 8 * ne / t_eq / 1e6, 1),
+                 "axpy_(4,3)_into_(5,4)_ms": round(t_ne, 3), "note": "unequal bandwidths also run the BandError counting pass over X and synchronise"}
+    del Xe, Ye, Yw
     out["TB"] = {"n": n, "k": N, "tbsv_U_ms": round(t_sv, 2), "tbmv_U_ms": round(t_mv, 3), "tbmv_GBs": round(by / t_mv / 1e6, 1),
                  "algorithmic_bytes": by}
     return out
