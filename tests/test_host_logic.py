@@ -76,3 +76,26 @@ def test_dimension_checks_before_any_kernel():
     R = bm.BandedMatrix(torch.zeros((7, 3), dtype=torch.float64), 6, 1, 1)
     with pytest.raises(bm.DimensionMismatch):  # non-square solve, test/test_bandedlu.jl:79-87
         bm.solve(R, torch.zeros(6, dtype=torch.float64))
+
+
+def test_new_wrappers_validate_before_touching_the_device():
+    """tbsv_/tbmv_/sbmv_/axpy_/copyto_ raise the reference's argument errors (src/blas.jl:86-93,124-131;
+    src/generic/broadcast.jl:979-983) from the host checks alone, and refuse CPU tensors instead of computing on them."""
+    A = bm.BandedMatrix(torch.zeros((6, 4), dtype=torch.float64), 6, 1, 2)   # 6 x 6, (l,u) = (1,2), CPU tensors
+    x = torch.zeros(6, dtype=torch.float64)
+    with pytest.raises(bm.DimensionMismatch):
+        bm.tbsv_("U", "N", "N", 7, 2, A.data[:, :3], x)                      # matrix is not square: dimensions are 6, 7
+    with pytest.raises(bm.DimensionMismatch):
+        bm.tbmv_("U", "N", "N", 6, 2, A.data[:, :3], x[:5])                  # size of A != length(x)
+    with pytest.raises(ValueError):
+        bm.tbsv_("U", "N", "N", 6, 3, A.data[:, :3], x)                      # triangular banded data missing
+    with pytest.raises(bm.DimensionMismatch):
+        bm.sbmv_("U", 2, 1.0, A.data[:, :3], x[:5], 0.0, x)
+    with pytest.raises(bm.DimensionMismatch):
+        bm.axpy_(1.0, A, bm.BandedMatrix(torch.zeros((5, 4), dtype=torch.float64), 6, 1, 2))
+    with pytest.raises(bm.DimensionMismatch):
+        bm.mul_sym_(x, "U", bm.BandedMatrix(torch.zeros((5, 4), dtype=torch.float64), 6, 1, 2), x)
+    with pytest.raises(TypeError):                                           # valid arguments, CPU tensors: no CPU fallback
+        bm.tbsv_("U", "N", "N", 6, 2, A.data[:, :3], x)
+    with pytest.raises(TypeError):
+        bm.axpy_(1.0, A, A)
