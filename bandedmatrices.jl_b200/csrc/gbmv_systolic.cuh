@@ -35,7 +35,6 @@ __device__ __forceinline__ void load_col(const double *__restrict__ a, i64 lda, 
 struct XPlain {
     const double *x;
     __device__ __forceinline__ void prepare(i64, int) const {}
-    __device__ __forceinline__ bool defer_first_set() const { return false; }
     __device__ __forceinline__ double stream(i64 c) const { return ld_stream(x + c); }
     __device__ __forceinline__ double plain(i64 c) const { return x[c]; }
 };
@@ -55,22 +54,9 @@ __device__ __forceinline__ void gbmv_n_systolic_body(i64 m, i64 n, int kl, int k
     const bool bz = (beta == 0.0);
     const int src = (lane + 31) & 31;
 
-    // Runs are independent (each recomputes its boundary rows in the prologue), so a run may be cut anywhere.  The sharded
-    // source uses that for run 0: its FIRST set needs the x halo the left neighbour pushes, so the rest of the run goes first
-    // and set 0 last -- the neighbour's start skew then hides behind a whole run of streaming instead of stalling it.
-    const i64 nparts_total = num_runs + ((xs.defer_first_set() && sets_per_run > 1 && total_sets > 1) ? 1 : 0);
-    for (i64 part = warp; part < nparts_total; part += nwarps) {
-        i64 set0, set1;
-        if (nparts_total > num_runs) {   // part 0 = run 0 without its first set; part num_runs = that first set, done last by warp (num_runs mod nwarps)
-            if (part == num_runs) { set0 = 0; set1 = 1; }
-            else {
-                set0 = part * sets_per_run + (part == 0 ? 1 : 0);
-                set1 = (part * sets_per_run + sets_per_run < total_sets) ? part * sets_per_run + sets_per_run : total_sets;
-            }
-        } else {
-            set0 = part * sets_per_run;
-            set1 = (set0 + sets_per_run < total_sets) ? set0 + sets_per_run : total_sets;
-        }
+    for (i64 run = warp; run < num_runs; run += nwarps) {
+        const i64 set0 = run * sets_per_run;
+        const i64 set1 = (set0 + sets_per_run < total_sets) ? set0 + sets_per_run : total_sets;
         const i64 cs = set0 * 32;
 
         // ---- prologue: partial chains of the W-1 rows that started before column cs ----

@@ -59,7 +59,6 @@ struct XHalo {
             }
         }
     }
-    __device__ __forceinline__ bool defer_first_set() const { return hl > 0; }
     __device__ __forceinline__ void prepare(i64 set_base, int) const
     {
         if (hl > 0 && set_base < hl) wait(flag_l);
