@@ -9,7 +9,7 @@
 //   * the LEADER CTA (cluster rank 0) owns the dependency chain.  Warp w takes the 16-row blocks t = w, w+GC_LW, ...: it
 //     receives the block from a worker (hand-off ring in its shared memory), applies the updates of the last GC_D
 //     panels as their solutions appear, solves the 16 x 16 diagonal triangle with shuffles, publishes the 16 solution
-//     entries in its own shared memory (next warp's input: plain doubles, CTA fence, tag), in global memory (the result)
+//     entries in its own shared memory (next warp's input: plain doubles + an mbarrier arrive), in global memory (the result)
 //     and in every worker's shared memory (DSMEM stores of self-validating 16-byte cells, no flags or fences).
 //   * the WORKER CTAs (ranks 1..C-1) stream the far part of the factors.  A warp owns two 16-row blocks from their
 //     birth (load of b) through all far panels (distance kl/16 .. GC_D+1 blocks from the diagonal), one row per lane,
@@ -128,6 +128,34 @@ __device__ __forceinline__ void gc_wait_local(const unsigned *tagp, unsigned wan
         if ((int)(tg - want) >= 0 || ab.tick()) return;
     }
 }
+__device__ __forceinline__ void gc_mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gc_mbar_arrive(unsigned long long *bar)
+{
+    unsigned long long st;
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// leader-local panel through the slot's mbarrier: the waiting warp is suspended by the hardware instead of spinning
+__device__ __forceinline__ void gc_read_local_mbar(const double *row, unsigned long long *bar, unsigned parity, double (&xv)[GC_NB], GcAbort &ab)
+{
+    if (ab.dead) return;
+    ab.spins = 0;
+    const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+    for (;;) {
+        unsigned done;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(ba), "r"(parity) : "memory");
+        if (done) break;
+        ab.spins += 0x3ffu;  // a failed try_wait has already slept for the hardware time-out
+        if (ab.tick()) return;
+    }
+    const unsigned ra = (unsigned)__cvta_generic_to_shared(row);
+#pragma unroll
+    for (int c = 0; c < GC_NB; c += 2)
+        asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2];" : "=d"(xv[c]), "=d"(xv[c + 1]) : "r"(ra + 8u * c) : "memory");
+}
 // wait until the slot's tag has reached `want` (tags only grow within a sweep): flow control, no data consumed
 __device__ __forceinline__ void gc_wait_tag(const GcCell *cell, unsigned want, GcAbort &ab)
 {
@@ -202,7 +230,8 @@ __device__ __forceinline__ double gc_apply(double acc, const double (&xp)[GC_NB]
 // hand-over costs 3-5 cycles of chain time.
 struct GcLocal {
     double xl[GC_HS][GC_NB];
-    unsigned ltag[GC_HS];
+    unsigned long long lbar[GC_HS];  // one mbarrier per ring slot: the warp that continues the chain SLEEPS on it (try_wait)
+    unsigned ltag[GC_HS];            // same information as a tag, for the prefetch warp (may lag more than a ring)
     long long pubclk[16];  // BMB200_GBTRS_STATS only
 };
 
@@ -214,7 +243,8 @@ struct GcLocal {
 // tbsv 'U' is <!FWD, DIV = non-unit>(kv=k, bw=k); tbsv 'L' is <FWD, DIV = non-unit>(kv=0, bw=k).
 template <bool FWD, bool DIV>
 __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *smem, int xslots, i64 n, int kv, int bw,
-                                         const double *__restrict__ ab, i64 ldab, double *x, int *gabort, int pfdist, long long *stats, GcLocal &loc)
+                                         const double *__restrict__ ab, i64 ldab, double *x, int *gabort, int pfdist, long long *stats, GcLocal &loc,
+                                         bool after_fwd = false)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, i = lane & 15;
     const i64 PB = (n + GC_NB - 1) / GC_NB;
@@ -229,6 +259,7 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
     long long (&pubclk)[16] = loc.pubclk;
     double (&xl)[GC_HS][GC_NB] = loc.xl;
     unsigned (&ltag)[GC_HS] = loc.ltag;
+    unsigned long long (&lbar)[GC_HS] = loc.lbar;
 
     if (rank == 0) {
         if (wid < GC_LW) {
@@ -290,7 +321,13 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
                     double xp[GC_NB];
                     GC_TICK(ca)
                     st[9] += ca - cl;
-                    gc_read_local(xl[s & (GC_HS - 1)], &ltag[s & (GC_HS - 1)], (unsigned)(s + 1) + fbase, xp, abt);
+                    {
+                        // phase of slot (s mod 16) for panel s: its uses so far = s/16 in this sweep, plus -- when a forward sweep
+                        // ran first on the same barriers -- one per forward panel that mapped to the slot
+                        const int sl16 = (int)(s & (GC_HS - 1));
+                        const i64 prev = (after_fwd && sl16 < PB) ? (PB - sl16 + GC_HS - 1) / GC_HS : 0;
+                        gc_read_local_mbar(xl[sl16], &lbar[sl16], (unsigned)((s / GC_HS + prev) & 1), xp, abt);
+                    }
                     GC_TICK(cb)
                     xi = gc_apply<FWD>(xi, xp, vc, mc);
                     GC_TICK(cc)
@@ -378,9 +415,11 @@ __device__ __forceinline__ void gc_sweep(cg::cluster_group &cluster, GcCell *sme
                 GcCell *mine = xs + (int)(t & xmask) * GC_NB + i;
                 if (stats && lane == 0) *(volatile long long *)&pubclk[t & 15] = c3;
                 if (lane < GC_NB) xl[t & (GC_HS - 1)][i] = xi;
-                asm volatile("fence.acq_rel.cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) *(volatile unsigned *)&ltag[t & (GC_HS - 1)] = mytag;
+                if (lane == 0) {
+                    gc_mbar_arrive(&lbar[t & (GC_HS - 1)]);  // release: the 16 stores above are visible to whoever the phase change wakes
+                    *(volatile unsigned *)&ltag[t & (GC_HS - 1)] = mytag;
+                }
                 if (lane < GC_NB && rowok) x[r] = xi;
                 // ... then every worker's ring (the two half-warps share the peers)
                 for (unsigned w = 1 + (lane >> 4); w < C; w += 2) gc_put_remote(mine, w, xi, mytag);
@@ -470,12 +509,13 @@ gbtrs_cluster_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 l
     double *x = bmat + (i64)(blockIdx.x / C) * ldb;
     __shared__ __align__(16) GcLocal loc;
     for (int k = threadIdx.x; k < (GC_HS + xslots) * GC_NB; k += blockDim.x) gc_smem[k] = GcCell{0u, 0u, 0u, 0u};
-    if (threadIdx.x < GC_HS) loc.ltag[threadIdx.x] = 0u;
+    if (threadIdx.x < GC_HS) { loc.ltag[threadIdx.x] = 0u; gc_mbar_init(&loc.lbar[threadIdx.x], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     cluster.sync();
     if (MODE == 0) {
         if (kl > 0) gc_sweep<true, false>(cluster, gc_smem, xslots, n, kl + ku, kl, ab, ldab, x, gabort, pfdist, stats, loc);
         cluster.sync();  // forward results are in global memory; every ring is quiescent
-        gc_sweep<false, true>(cluster, gc_smem, xslots, n, kl + ku, kl + ku, ab, ldab, x, gabort, pfdist, stats, loc);
+        gc_sweep<false, true>(cluster, gc_smem, xslots, n, kl + ku, kl + ku, ab, ldab, x, gabort, pfdist, stats, loc, kl > 0);
     } else if (MODE == 1) {
         gc_sweep<false, false>(cluster, gc_smem, xslots, n, ku, ku, ab, ldab, x, gabort, pfdist, stats, loc);
     } else if (MODE == 2) {
