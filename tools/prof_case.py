@@ -33,3 +33,24 @@ elif what == "widelu":
         x = torch.ones(n, dtype=torch.float64, device="cuda")
         bm.ldiv_(F, x)
     torch.cuda.synchronize()
+elif what == "tb":
+    k = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    d = torch.rand((n, k + 1), dtype=torch.float64, device="cuda") / (2 * k)
+    d[:, k] = 2.0
+    x = torch.ones(n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        bm.tbmv_("U", "N", "N", n, k, d, x)
+    torch.cuda.synchronize()
+elif what == "sbmv":
+    k = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    d = torch.rand((n, k + 1), dtype=torch.float64, device="cuda")
+    x = torch.rand(n, dtype=torch.float64, device="cuda")
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        bm.sbmv_("U", k, 1.0, d, x, 0.0, y)
+    torch.cuda.synchronize()
+elif what == "axpy":
+    X, Y = bm.brand(n, n, 4, 3, seed=1), bm.brand(n, n, 4, 3, seed=2)
+    for _ in range(2):
+        bm.axpy_(0.5, X, Y)
+    torch.cuda.synchronize()
