@@ -46,6 +46,14 @@ PROTOTYPES = {
     "bmb200_dgbmv_sharded": (C.c_int, [vp, i64, i64, i64, i64, i64, dbl, vp, i64, vp, dbl, vp]),
 }
 
+# test / tuning hooks of include/bmb200_internal.h (not part of the drop-in ABI)
+INTERNAL_PROTOTYPES = {
+    "bmb200_internal_divcheck": (C.c_int, [vp, i64, vp, vp, vp]),
+    "bmb200_internal_divcheck2": (C.c_int, [vp, i64, vp, vp, vp]),
+    "bmb200_internal_set_tuning": (C.c_int, [vp, C.c_char_p, C.c_longlong]),
+    "bmb200_internal_gbtrs_slot": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, i64, i64, i64, i64, vp, i64, vp, vp, i64]),
+}
+
 _lib = None
 
 
@@ -59,7 +67,7 @@ def load() -> C.CDLL:
                 "(make -C bandedmatrices.jl_b200/csrc).  There is no CPU fallback."
             )
         lib = C.CDLL(LIB_PATH)
-        for name, (res, args) in PROTOTYPES.items():
+        for name, (res, args) in list(PROTOTYPES.items()) + list(INTERNAL_PROTOTYPES.items()):
             fn = getattr(lib, name)  # AttributeError here == header/library drift
             fn.restype = res
             fn.argtypes = args
@@ -89,6 +97,10 @@ class Handle:
 
     def set_stream(self, stream_ptr: int) -> None:
         self.check(self.lib.bmb200_set_stream(self.h, vp(stream_ptr) if stream_ptr else None), "set_stream")
+
+    def tune(self, key: str, value: int) -> None:
+        """Development knob of this handle (include/bmb200_internal.h); ``tune("reset", 0)`` restores the defaults."""
+        self.check(self.lib.bmb200_internal_set_tuning(self.h, key.encode(), int(value)), f"set_tuning({key})")
 
     def sync(self) -> None:
         self.check(self.lib.bmb200_sync(self.h), "sync")

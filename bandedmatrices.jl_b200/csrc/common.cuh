@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "../../include/bmb200.h"
+#include "../../include/bmb200_internal.h"
 
 typedef int64_t i64;
 
@@ -22,7 +23,28 @@ struct bmb200_halo {
     unsigned long long epoch = 0;
 };
 
+// Development knobs (A/B timing, diagnostics).  Release dispatch reads ONLY this block -- never the environment; the
+// defaults below are the shipped behaviour and bmb200_internal_set_tuning (include/bmb200_internal.h) is the only writer.
+struct bmb_tuning {
+    int gbmm_ring = -1;        // 1 forces the persistent ring kernel for banded x banded, 0 disables it
+    int gbmm_nt = 3;           // row tiles per work item (2 or 3)
+    int gbmm_rw = 0;           // ring kernel warps per CTA (0 = by tile width)
+    int gbtrf_nopipe = 0;      // 1 disables the pipelined wide-band LU
+    long long pipe_maxpanels = 0;  // > 0 caps the panels the pipelined LU takes
+    int pipe_nospec = 0;       // 1 disables optimistic diagonal pivoting
+    int pipe_stats = 0;        // 1 prints the chain CTA's cycle breakdown
+    int gbtrs_noblock = 0;     // 1 disables the panel-blocked interchange-free solve
+    int gbtrs_pfdist_blocked = 1;
+    int gbtrs_nocluster = 0;   // 1 disables the cluster solve
+    int gbtrs_cluster = 0;     // > 0 forces the cluster size
+    int gbtrs_pfdist = 6;      // L2 prefetch distance (panels) of the cluster solve
+    int gbtrs_stats = 0;
+    int debug = 0;
+    int sbmv_rows_k = 16;      // band width below which dsbmv uses the row kernel
+};
+
 struct bmb200_ctx {
+    bmb_tuning tune;
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;

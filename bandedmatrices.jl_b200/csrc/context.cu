@@ -181,3 +181,22 @@ extern "C" int bmb200_dband_widen(bmb200_handle_t h, int64_t n, int64_t l, int64
     BMB_LAUNCH_CHECK(h);
     return 0;
 }
+
+// ---- development hook (include/bmb200_internal.h): the only writer of the handle's tuning block ----
+extern "C" int bmb200_internal_set_tuning(bmb200_handle_t h, const char *key, long long value)
+{
+    if (!h || !key) return -1;
+    bmb_tuning &t = h->tune;
+    struct { const char *name; int *slot; } ints[] = {
+        {"gbmm_ring", &t.gbmm_ring}, {"gbmm_nt", &t.gbmm_nt}, {"gbmm_rw", &t.gbmm_rw}, {"gbtrf_nopipe", &t.gbtrf_nopipe},
+        {"pipe_nospec", &t.pipe_nospec}, {"pipe_stats", &t.pipe_stats}, {"gbtrs_noblock", &t.gbtrs_noblock},
+        {"gbtrs_pfdist_blocked", &t.gbtrs_pfdist_blocked}, {"gbtrs_nocluster", &t.gbtrs_nocluster},
+        {"gbtrs_cluster", &t.gbtrs_cluster}, {"gbtrs_pfdist", &t.gbtrs_pfdist}, {"gbtrs_stats", &t.gbtrs_stats},
+        {"debug", &t.debug}, {"sbmv_rows_k", &t.sbmv_rows_k},
+    };
+    for (auto &e : ints)
+        if (strcmp(key, e.name) == 0) { *e.slot = (int)value; return 0; }
+    if (strcmp(key, "pipe_maxpanels") == 0) { t.pipe_maxpanels = value; return 0; }
+    if (strcmp(key, "reset") == 0) { t = bmb_tuning(); return 0; }
+    return -2;
+}

@@ -493,8 +493,8 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
         const int PA = pitch5((int)WA + 2 * GM_PAD), PB = pitch5((int)WB + 2 * GM_PAD);
         // Two tensor-core kernels: the two-CTA-per-SM tile kernel while a tile's staged columns fit in half an SM's shared
         // memory (C3: 4.45 ms), else the persistent ring kernel (one CTA per SM; C3: 4.63 ms, (64,64)x(64,64): 12.4 ms
-        // where the sweep kernel took 110 ms).  BMB200_GBMM_RING=1 forces the ring kernel, =0 disables it.
-        static const int ring_env = getenv("BMB200_GBMM_RING") ? atoi(getenv("BMB200_GBMM_RING")) : -1;
+        // where the sweep kernel took 110 ms).  tune.gbmm_ring = 1 forces the ring kernel, 0 disables it.
+        const int ring_env = h->tune.gbmm_ring;
         const bool tile_fits = ((size_t)(GM_TJ + Bl + Bu + 7) * PA + (size_t)GM_TJ * PB) * sizeof(double) <= 110 * 1024;
         const bool try_ring = ring_env == 1 || (ring_env != 0 && !tile_fits);
         for (int TJ = 32; TJ >= 8 && try_ring && jsplit == 0; TJ >>= 1) {  // ring kernel: widest tile whose ring fits
@@ -506,7 +506,7 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
             const i64 blocks = imin64(ntiles, (i64)h->sm_count);
             const i64 tpc = cdiv64(ntiles, blocks);
             if (tpc * TJ + Bl + Bu + 64 >= ((i64)1 << 31)) break;
-            static const int rnt = getenv("BMB200_GBMM_NT") ? atoi(getenv("BMB200_GBMM_NT")) : 3;  // tuning switch
+            const int rnt = h->tune.gbmm_nt;
 #define GR_LAUNCH(NT, TH)                                                                                                              \
     do {                                                                                                                               \
         BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_ring<NT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));             \
@@ -515,7 +515,7 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
                                                                                        dB, ldb, beta, dC, ldc, PA, PB, NAr, RS,       \
                                                                                        TJ, ntiles, tpc);                              \
     } while (0)
-            static const int rw_env = getenv("BMB200_GBMM_RW") ? atoi(getenv("BMB200_GBMM_RW")) : 0;  // warps per CTA (tuning switch)
+            const int rw_env = h->tune.gbmm_rw;  // warps per CTA
             const int rw = rw_env ? rw_env : (TJ >= 16 ? 16 : 12);
             if (rw == 12) { if (rnt == 2) GR_LAUNCH(2, 384); else GR_LAUNCH(3, 384); }
             else { if (rnt == 2) GR_LAUNCH(2, 512); else GR_LAUNCH(3, 512); }
@@ -528,7 +528,7 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
         if (jsplit == 0 && smem <= 110 * 1024) {
             const i64 ntiles = cdiv64(mprod, GM_TJ);
             const i64 blocks = imin64(ntiles, (i64)h->sm_count * 2);
-            static const int nt_env = getenv("BMB200_GBMM_NT") ? atoi(getenv("BMB200_GBMM_NT")) : 3;  // tuning switch
+            const int nt_env = h->tune.gbmm_nt;
 #define GM_LAUNCH(NT)                                                                                                          \
     do {                                                                                                                       \
         BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_dmma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \

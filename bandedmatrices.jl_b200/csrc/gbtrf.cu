@@ -15,7 +15,6 @@
 //                  merit is ns per column, not a roofline fraction.
 //   (wide bands: gbtrf_blocked.cu)
 #include "common.cuh"
-#include <stdlib.h>
 
 int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv);
 int bmb_gbtrf_reg(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv);  // gbtrf_reg.cu
@@ -160,153 +159,6 @@ gbtrf_window(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i6
 }
 
 // ------------------------------------------------------------------------------------------------
-// gbtrf_warp<NC>: one warp, everything in registers (kl <= 31, kl+ku+1 <= NC <= 64).
-//   lane = one ACTIVE ROW of the (kl+1)-row window, registers a[NC] = its entries in columns j..j+NC-1
-//   (column c lives in a[c % NC]; the step loop is unrolled NC-fold so every index is a constant).
-//   * IDAMAX  = three warp REDUX ops on the bit pattern of |v| (hi word, lo word, then min position => FIRST max)
-//   * DSWAP   = relabelling: rows never move between lanes, only their position numbers are exchanged
-//   * DSCAL   = v * (1/pivot); every lane computes the reciprocal of its own candidate while the REDUX chain runs
-//   * DGER    = pivot row published through shared memory, one FMA per (row, column): a = fma(-u, l, a)
-//   * the retired pivot row is the finished U row: written to AB by all lanes from shared memory; the freed lane
-//     picks up the next matrix row from a cp.async-fed ring of incoming columns.
-// No block barrier and no global latency on the chain of dependent pivot steps.
-// ------------------------------------------------------------------------------------------------
-#define GBW_PF 16
-
-template <int NC>
-__global__ void __launch_bounds__(32, 1)
-gbtrf_warp(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i64 *__restrict__ ipiv,
-           int *__restrict__ d_info, int rmask)
-{
-    extern __shared__ double sm[];
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr int RP = (NC + 1) & ~1;  // ring row pitch (even => 16-byte aligned rows)
-    const int lane = threadIdx.x;
-    const int kv = kl + ku, nb = kl + ku + 1;  // nb = original band entries per row / per column
-    // ring of incoming matrix ROWS (row-major, entries [0,nb) live, [nb,RP) permanently zero): the cp.async that
-    // fetches band column c scatters its entries to the rows they belong to, so an entering row is read back as
-    // contiguous doubles with no index arithmetic.
-    double *ring = sm;                                  // (rmask+1) x RP
-    double *urow = sm + (size_t)(rmask + 1) * RP;       // RP : the pivot row of the current step
-    const i64 mn = m < n ? m : n;
-    int info = 0;
-
-    for (int t = lane; t < (rmask + 1) * RP + RP; t += 32) sm[t] = 0.0;
-    __syncwarp();
-
-    // per-lane fetch state for band entries d = lane and d = lane+32 of the column being fetched (all incremental:
-    // no multiplications or 64-bit index arithmetic on the per-step path)
-    i64 fc = 0;                                           // next column to fetch
-    const bool has0 = lane < nb, has1 = lane + 32 < nb;
-    i64 fr0 = (i64)lane - ku, fr1 = (i64)lane + 32 - ku;  // matrix row of entry d in column fc
-    const double *fs0 = ab + (kl + lane), *fs1 = ab + (kl + lane + 32);
-    auto fetch = [&]() {  // entry (r, fc) lands at ring[(r & rmask)*RP + (kv - d)]
-        if (has0 && fr0 >= 0 && fr0 < m) {
-            double *dst = ring + ((int)fr0 & rmask) * RP + (kv - lane);
-            if (fc < n) cp_async8(dst, fs0);
-            else *dst = 0.0;  // virtual column right of the matrix
-        }
-        if (has1 && fr1 >= 0 && fr1 < m) {
-            double *dst = ring + ((int)fr1 & rmask) * RP + (kv - lane - 32);
-            if (fc < n) cp_async8(dst, fs1);
-            else *dst = 0.0;
-        }
-        ++fc; ++fr0; ++fr1;
-        fs0 += ldab; fs1 += ldab;
-    };
-
-    for (int c = 0; c < kv + 1 + GBW_PF; ++c) fetch();
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
-
-    double a[NC];
-    i64 pos = (lane <= kl && lane < m) ? lane : -1;  // absolute row held by this lane, -1 = idle
-#pragma unroll
-    for (int c = 0; c < NC; ++c)  // row r = lane: column c sits at ring offset c - r + kl
-        a[c] = (pos >= 0 && c <= lane + ku && c < n) ? ring[lane * RP + (c - lane + kl)] : 0.0;
-
-    double *pcol = ab + kv;                       // &AB(kv, j): diagonal slot of column j
-    const i64 ustride = ldab - 1;                 // U row j walks AB with this stride
-    const i64 uoff0 = (i64)lane * ustride, uoff1 = (i64)(lane + 32) * ustride;
-    for (i64 jb = 0; jb < mn; jb += NC) {
-#pragma unroll
-        for (int ph = 0; ph < NC; ++ph) {
-            const i64 j = jb + ph;
-            if (j < mn) {
-                fetch();  // column j + kv + 1 + PF
-                cp_async_commit();
-                cp_async_wait<GBW_PF>();
-                __syncwarp();
-                const bool act = pos >= 0;
-                const double v = a[ph];
-                // ---- IDAMAX: first maximum of |v| over the active rows ----
-                const unsigned long long key = act ? (unsigned long long)__double_as_longlong(fabs(v)) : 0ull;
-                const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-                const double rown = 1.0 / v;  // own reciprocal, overlapped with the reductions
-                const unsigned mhi = __reduce_max_sync(FULL, hi);
-                const bool c1 = act && hi == mhi;
-                const unsigned mlo = __reduce_max_sync(FULL, c1 ? lo : 0u);
-                const bool c2 = c1 && lo == mlo;
-                const unsigned rel = act ? (unsigned)(pos - j) : 0xffffffffu;
-                const int jp = (int)__reduce_min_sync(FULL, c2 ? rel : 0xffffffffu);
-                const int pl = __ffs(__ballot_sync(FULL, c2 && rel == (unsigned)jp)) - 1;  // pivot lane
-                const int lj = __ffs(__ballot_sync(FULL, act && rel == 0u)) - 1;           // lane holding row j
-                const double pv = shfl_d(v, pl);
-                const double rinv = shfl_d(rown, pl);
-                if (lane == 0) ipiv[j] = j + jp + 1;
-                if (pv == 0.0 && info == 0) info = (int)(j + 1);
-                // ---- DSWAP by relabelling ----
-                if (lane == lj) pos = j + jp;
-                if (lane == pl) pos = j;
-                // ---- publish the pivot row ----
-                if (lane == pl) {
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) urow[c] = a[(ph + c) % NC];
-                }
-                __syncwarp();
-                // ---- DSCAL + DGER (a zero pivot leaves the column untouched, like DGBTF2) ----
-                const double l = (pv != 0.0) ? __dmul_rn(v, rinv) : v;
-                if (act && lane != pl) pcol[(int)(pos - j)] = l;
-                const double2 *u2 = reinterpret_cast<const double2 *>(urow);
-#pragma unroll
-                for (int c = 0; c < NC; c += 2) {  // idle / pivot lanes compute garbage that is never used
-                    const double2 u = u2[c >> 1];
-                    if (c >= 1) a[(ph + c) % NC] = fma(-u.x, l, a[(ph + c) % NC]);
-                    if (c + 1 < NC) a[(ph + c + 1) % NC] = fma(-u.y, l, a[(ph + c + 1) % NC]);
-                }
-                a[ph] = 0.0;  // this register now stands for column j+NC, structurally zero for every resident row
-                // ---- the finished U row goes out (all kv+1 entries: this also writes the fill-in zeros) ----
-                if (lane <= kv && j + lane < n) pcol[uoff0] = urow[lane];
-                if (lane + 32 <= kv && j + lane + 32 < n) pcol[uoff1] = urow[lane + 32];
-                // ---- the freed lane takes the next matrix row (columns j+1 .. ; zeros beyond its band) ----
-                const i64 rnew = j + kl + 1;
-                if (lane == pl) {
-                    pos = (rnew < m) ? rnew : -1;
-                    const double *src = ring + ((int)rnew & rmask) * RP;
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) a[(ph + 1 + c) % NC] = src[c];
-                }
-                __syncwarp();  // urow / ring rows are reused by the next step
-                pcol += ldab;
-            }
-        }
-    }
-    cp_async_wait<0>();
-    if (lane == 0) d_info[0] = info;
-}
-
-template <int NC>
-static int launch_gbtrf_warp(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv)
-{
-    int rows = 32;
-    while (rows < kl + ku + 1 + GBW_PF + 2) rows <<= 1;  // ring rows (power of two)
-    const size_t smem = ((size_t)rows + 1) * ((NC + 1) & ~1) * sizeof(double);
-    BMB_CUDA(h, cudaFuncSetAttribute(gbtrf_warp<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gbtrf_warp<NC><<<1, 32, smem, h->stream>>>(m, n, (int)kl, (int)ku, dAB, ldab, d_ipiv, h->d_info, rows - 1);
-    BMB_LAUNCH_CHECK(h);
-    return 0;
-}
 
 extern "C" int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, double *dAB,
                              int64_t ldab, int64_t *d_ipiv, int *info)
@@ -327,17 +179,8 @@ extern "C" int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl
     const int nslot = (int)(kv + GBTRF_PF + 2);
     const size_t smem = ((size_t)nslot * ldw + 2 * (kv + 1) + (kl + 1)) * sizeof(double);
     int rc;
-    static const bool old_warp = getenv("BMB200_GBTRF_OLD") != nullptr;  // development switch (A/B timing)
-    if (kl <= 31 && kv + 1 <= 33 && !old_warp) {  // software-pipelined register kernel (gbtrf_reg.cu)
+    if (kl <= 31 && kv + 1 <= 33) {  // software-pipelined register kernel (gbtrf_reg.cu)
         rc = bmb_gbtrf_reg(h, m, n, kl, ku, dAB, ldab, d_ipiv);
-        if (rc) return rc;
-    } else if (kl <= 31 && kv + 1 <= 33) {  // first-generation register kernel
-        const i64 w = kv + 1;
-        if (w <= 4) rc = launch_gbtrf_warp<4>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
-        else if (w <= 8) rc = launch_gbtrf_warp<8>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
-        else if (w <= 16) rc = launch_gbtrf_warp<16>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
-        else if (w <= 24) rc = launch_gbtrf_warp<24>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
-        else rc = launch_gbtrf_warp<33>(h, m, n, kl, ku, dAB, ldab, d_ipiv);
         if (rc) return rc;
     } else if (smem <= 220 * 1024) {
         BMB_CUDA(h, cudaFuncSetAttribute(gbtrf_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

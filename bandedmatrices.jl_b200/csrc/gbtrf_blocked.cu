@@ -85,6 +85,7 @@ gbtrf_panel(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, i64
                 if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
             }
             if (lane == 0) {
+                if (bidx > jj + km) bidx = jj;  // every candidate was NaN (v > best never held): keep the diagonal, stay in bounds
                 s_piv = bidx;
                 ipiv[j] = J + bidx + 1;
                 if (pc[bidx] != 0.0) {

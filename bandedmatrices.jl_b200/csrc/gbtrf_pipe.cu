@@ -27,7 +27,6 @@
 // to DGBTF2 (LAPACK's blocked DGBTRF, which OpenBLAS runs for ku > 64, differs from that only by DGEMM rounding).
 #include <climits>
 #include <cooperative_groups.h>
-#include <stdlib.h>
 
 #include <vector>
 
@@ -230,7 +229,7 @@ __device__ __forceinline__ unsigned gp_argmax(unsigned long long key, unsigned r
 template <int NB>
 __device__ void gp_chain(const PipeArgs &A, double *smem)
 {
-    const bool getenv_spec = A.speculate != 0;
+    const bool want_spec = A.speculate != 0;
     constexpr int RPT = GP_RPT, NT = GP_NT, NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int kl = A.kl, ku = A.ku, kv = kl + ku, R = NB + kl, PY = A.PY;
@@ -295,7 +294,7 @@ __device__ void gp_chain(const PipeArgs &A, double *smem)
     if (tid == 0) { s_flag[0] = 1; s_flag[1] = 0; }
     __syncthreads();
     double *gbase = ab + kv + tid;   // AB(kv + r - jj, j) of row r = tid at the current step; advanced by ldab-1 per step
-    bool speculate = getenv_spec;
+    bool speculate = want_spec;
     long long nopt = 0;
     int pollv0 = 0, pollv1 = 0;      // thread 0: progress flags of the next block, loaded one phase early
 
@@ -491,12 +490,16 @@ __device__ void gp_chain(const PipeArgs &A, double *smem)
             const i64 j = J + jj;
             const int pb = jj & 1;
             // ---- thread-local candidate: first maximum over this thread's active rows ----
+            // (compared through the bit pattern of |v|, like gp_argmax: a NaN ranks above every number, so a column
+            // whose candidates are all NaN still yields a pivot row instead of "no candidate")
             double bsv = 0.0, bav = -1.0;
+            long long bkey = -1;
             int bq = -1;
 #pragma unroll
             for (int q = 0; q < RPT; ++q) {
                 const double v = X[q][jj], av = fabs(v);
-                if (((actm[q] >> jj) & 1u) && av > bav) { bav = av; bsv = v; bq = q; }
+                const long long key = __double_as_longlong(av);
+                if (((actm[q] >> jj) & 1u) && key > bkey) { bkey = key; bav = av; bsv = v; bq = q; }
             }
             const double rown = 1.0 / bsv;  // own reciprocal, overlapped with the reductions
             const int br = (bq >= 0) ? tid + bq * NT : INT_MAX;
@@ -868,15 +871,14 @@ static int pitch_mod16(int need, int rem)  // smallest p >= need with p = rem (m
 int bmb_gbtrf_pipe(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv, i64 *Jdone)
 {
     *Jdone = 0;
-    static const bool off = getenv("BMB200_GBTRF_NOPIPE") != nullptr;
-    if (off) return 0;
+    if (h->tune.gbtrf_nopipe) return 0;
     constexpr int NB = GP_NB, CG = GP_CG;
     const i64 R = NB + kl;
     if (kl < 32 || ku < 2 * NB || R > (i64)GP_RPT * GP_NT) return 0;
     // every pipelined panel k needs rows up to J + 2NB + kl - 1 and the whole block k+1 (+ one element of slack)
     i64 KP = imin64((m - kl - 2 * NB) / NB + 1, (n - 1) / NB - 1);
     if (m - kl - 2 * NB < 0) KP = 0;
-    if (const char *e = getenv("BMB200_PIPE_MAXPANELS")) KP = imin64(KP, atoll(e));
+    if (h->tune.pipe_maxpanels > 0) KP = imin64(KP, h->tune.pipe_maxpanels);
     if (KP < 4) return 0;
     const int NT = GP_NT;
     const int KLP = (int)((kl + 7) & ~7);
@@ -913,10 +915,10 @@ int bmb_gbtrf_pipe(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64
     a.ring = (double *)((char *)h->scratch + ctl_bytes);
     a.slot_doubles = slot_doubles;
     a.PY = PY; a.PX = PX; a.KLP = KLP;
-    a.speculate = getenv("BMB200_PIPE_NOSPEC") ? 0 : 1;
+    a.speculate = h->tune.pipe_nospec ? 0 : 1;
     a.stats = (long long *)((char *)h->scratch + flag_bytes);
     void *args[] = {(void *)&a};
-    static const bool show = getenv("BMB200_PIPE_STATS") != nullptr;
+    const bool show = h->tune.pipe_stats != 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (show) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
     BMB_CUDA(h, cudaLaunchCooperativeKernel((const void *)gbtrf_pipe_kernel, dim3(grid), dim3(NT), args, smem, h->stream));

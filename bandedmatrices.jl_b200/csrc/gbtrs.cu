@@ -9,12 +9,11 @@
 // RHS columns whose active window lives in a shared-memory ring; lanes span the band; the L / U
 // column of the NEXT steps is prefetched into registers so that no global latency sits on the chain.
 #include "common.cuh"
-#include <stdlib.h>
 
 #define GBTRS_WARPS 4
 
-int bmb_gbtrs_lane(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
-                   double *dB, i64 ldb);  // gbtrs_lane.cu
+int bmb_gbtrs_slot(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
+                   double *dB, i64 ldb);  // gbtrs_slot.cu
 int bmb_gbtrs_shfl(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
                    double *dB, i64 ldb);
 int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb);  // gbtrs_shfl.cu
@@ -408,11 +407,14 @@ extern "C" int bmb200_dgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t k
         BMB_LAUNCH_CHECK(h);
         return 0;
     }
+    // narrow bands (kl <= 28, kl+ku <= 32; C1, C4): slot-scheduled sweeps, P steps per shuffle round (gbtrs_slot.cu)
+    {
+        const int rc = bmb_gbtrs_slot(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+        if (rc != 1) return rc;
+    }
     // bands up to (63, 127-kl): window in registers across the lanes of a warp (gbtrs_shfl.cu)
     {
-        static const bool use_lane = getenv("BMB200_GBTRS_LANE") != nullptr;  // development switch (A/B timing)
-        const int rc = use_lane ? bmb_gbtrs_lane(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb)
-                                : bmb_gbtrs_shfl(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+        const int rc = bmb_gbtrs_shfl(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
         if (rc != 1) return rc;
     }
     // KPL covers kl (forward) and 2*KPL+1 covers kv = kl+ku (backward): need 32*KPL >= kl and 32*(2KPL+1) >= kv

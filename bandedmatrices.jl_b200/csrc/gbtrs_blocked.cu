@@ -248,7 +248,7 @@ static int launch_noswap(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const d
     while (ring < kl + ku + 1 + 3 * GB_THREADS) ring <<= 1;
     const size_t smem = (size_t)ring * sizeof(double);
     BMB_CUDA(h, cudaFuncSetAttribute(gbtrs_wide_noswap<KPL, KPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static const int pfdist = getenv("BMB200_GBTRS_PFDIST") ? atoi(getenv("BMB200_GBTRS_PFDIST")) : 1;
+    const int pfdist = h->tune.gbtrs_pfdist_blocked;
     gbtrs_wide_noswap<KPL, KPU><<<(unsigned)nrhs, GB_THREADS, smem, h->stream>>>(n, (int)kl, (int)ku, dAB, ldab, dB, ldb, ring, pfdist);
     BMB_LAUNCH_CHECK(h);
     return 0;
@@ -259,8 +259,7 @@ int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doub
 // returns 1 when not applicable (the caller then runs the general kernel), 0 on success, <0 on error
 int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb)
 {
-    static const bool off = getenv("BMB200_GBTRS_NOBLOCK") != nullptr;
-    if (off) return 1;
+    if (h->tune.gbtrs_noblock) return 1;
     int *cnt = h->d_info + 16;
     BMB_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int), h->stream));
     gbtrs_count_interchanges<<<h->sm_count, 256, 0, h->stream>>>(n, d_ipiv, cnt);

@@ -530,10 +530,8 @@ gbtrs_cluster_noswap(i64 n, int kl, int ku, const double *__restrict__ ab, i64 l
 // mode 0: the caller has verified ipiv = 1:n.  modes 1-3: triangular band solves (see the kernel).
 int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb)
 {
-    static const bool off = getenv("BMB200_GBTRS_NOCLUSTER") != nullptr;
-    static const int csize_env = getenv("BMB200_GBTRS_CLUSTER") ? atoi(getenv("BMB200_GBTRS_CLUSTER")) : 0;
-    static const int pfdist = getenv("BMB200_GBTRS_PFDIST") ? atoi(getenv("BMB200_GBTRS_PFDIST")) : 6;
-    if (off) return 1;
+    const int csize_env = h->tune.gbtrs_cluster, pfdist = h->tune.gbtrs_pfdist;
+    if (h->tune.gbtrs_nocluster) return 1;
     const i64 kv = kl + ku;
     if (n >= ((i64)1 << 33)) return 1;  // flag arithmetic is 32-bit
     const int KBmax = (int)((kv + GC_NB - 1) / GC_NB);
@@ -567,12 +565,12 @@ int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, 
         cfg.numAttrs = 1;
         int nclusters = 0;
         const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
-        static const bool dbg = getenv("BMB200_DEBUG") != nullptr;
+        const bool dbg = h->tune.debug != 0;
         if (dbg) fprintf(stderr, "[bmb200] gbtrs_cluster: cluster size %d -> %s, %d co-resident clusters, smem %zu\n", csize, cudaGetErrorString(e), nclusters, smem);
         if (e == cudaSuccess && nclusters > 0) break;
         (void)cudaGetLastError();
     }
-    static const bool want_stats = getenv("BMB200_GBTRS_STATS") != nullptr;  // development aid: cycle breakdown of leader warp 0
+    const bool want_stats = h->tune.gbtrs_stats != 0;  // development aid: cycle breakdown of leader warp 0
     long long *dstats = nullptr;
     if (want_stats) {
         if (bmb_ensure_scratch(h, 24 * sizeof(long long)) != 0) return BMB200_ERR_CUDA;

@@ -155,8 +155,10 @@ static int launch_sharded(bmb200_ctx *h, i64 ms, i64 ns, i64 kls, i64 kus, doubl
                           XHalo xs, double beta, double *dy, HaloBox L, HaloBox R, int push_l, int push_r, int par)
 {
     const int threads = 256;
-    int per_sm = 0;
-    BMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gbmv_n_systolic_sharded<W, LDV>, threads, 0));
+    static int per_sm_cached = 0;  // a property of the kernel image: queried once per instantiation, not per call
+    if (per_sm_cached == 0)
+        BMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, gbmv_n_systolic_sharded<W, LDV>, threads, 0));
+    const int per_sm = per_sm_cached;
     const SystolicPlan p = systolic_plan(ms, kus, h->sm_count, per_sm, threads);
     gbmv_n_systolic_sharded<W, LDV><<<(unsigned)p.blocks, threads, 0, h->stream>>>(
         ms, ns, (int)kls, (int)kus, alpha, dA, lda, xs, beta, dy, p.total_sets, p.sets_per_run, p.num_runs, L, R, push_l,
@@ -202,7 +204,12 @@ extern "C" int bmb200_dgbmv_sharded(bmb200_handle_t h, int64_t n_global, int64_t
     const i64 cs = imax64(0, c0 - kl), ce = imin64(n_global, c1 + ku);
     const i64 hl = c0 - cs, hr = ce - c1;
     const i64 ms = nl, ns = ce - cs, kus = ku + hl, kls = kl - hl;
-    H.epoch += 1;
+    if ((hl > 0 && !H.left_box) || (hr > 0 && !H.right_box)) {
+        snprintf(h->err, sizeof(h->err), "dgbmv_sharded: slab [%lld,%lld) needs a neighbour that is not connected",
+                 (long long)c0, (long long)c1);
+        return BMB200_ERR_CUDA;
+    }
+    H.epoch += 1;  // only once every validation has passed: a failed call must not desynchronise the ranks' epochs
     const int par = (int)(H.epoch & 1);
     HaloBox own{H.box, H.max_halo}, L{H.left_box, H.max_halo}, R{H.right_box, H.max_halo};
     XHalo xs;
@@ -219,11 +226,6 @@ extern "C" int bmb200_dgbmv_sharded(bmb200_handle_t h, int64_t n_global, int64_t
     // what the neighbours need from me: the left rank reads my first ku entries, the right rank my last kl entries
     const int push_l = (H.left_box && c0 > 0) ? (int)ku : 0;
     const int push_r = (H.right_box && c1 < n_global) ? (int)kl : 0;
-    if ((hl > 0 && !H.left_box) || (hr > 0 && !H.right_box)) {
-        snprintf(h->err, sizeof(h->err), "dgbmv_sharded: slab [%lld,%lld) needs a neighbour that is not connected",
-                 (long long)c0, (long long)c1);
-        return BMB200_ERR_CUDA;
-    }
     // (alpha == 0 still runs the kernel: the epoch must be published or the neighbours would wait for this rank)
     const bool vec = (lda == 8) && (((uintptr_t)dA_local & 31) == 0);
     const int W = (int)(kl + ku + 1);

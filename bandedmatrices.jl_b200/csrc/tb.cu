@@ -285,7 +285,7 @@ extern "C" int bmb200_dsbmv(bmb200_handle_t h, char uplo, int64_t n, int64_t k, 
     if (!dA || !dx || !dy) return -6;
     if (dx == dy) return -8;  // the reference un-aliases x and y before the call (symbanded.jl:77-83)
     DeviceGuard g(h->device);
-    static const int kthr = getenv("BMB200_SBMV_ROWS_K") ? atoi(getenv("BMB200_SBMV_ROWS_K")) : 16;  // tuning switch
+    const int kthr = h->tune.sbmv_rows_k;
     if (k < kthr) {
         const i64 blocks = imin64(cdiv64(n, 256), (i64)h->sm_count * 16);
         if (up) sbmv_rows<true><<<(unsigned)blocks, 256, 0, h->stream>>>(n, (int)k, alpha, dA, lda, dx, beta, dy);

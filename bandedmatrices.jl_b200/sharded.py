@@ -91,3 +91,116 @@ class ShardedGbmv:
 
     def close(self):
         self.hd.lib.bmb200_halo_destroy(self.hd.h)
+
+    def check(self) -> None:
+        """Synchronise and raise if a halo wait timed out (the kernel flags it and carries on with stale data)."""
+        self.hd.sync()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LU / solve: the factorisation does not partition (ipiv must be bit-identical), the solve shards over RIGHT-HAND SIDES
+# (SURVEY.md 8e; reference site ldiv!(::BandedLU, B), src/banded/linalg.jl:24-30).  Factor once, broadcast the factors
+# and the pivots, then every rank runs bmb200_dgbtrs on its own block of B's columns: no exchange during the solve.
+# ---------------------------------------------------------------------------------------------------------------------
+def rhs_bounds(nrhs: int, rank: int, world: int):
+    """Contiguous block [q0, q1) of right-hand-side columns owned by ``rank``."""
+    return (nrhs * rank) // world, (nrhs * (rank + 1)) // world
+
+
+def broadcast_factors(data: torch.Tensor, ipiv: torch.Tensor, src: int = 0, group=None):
+    """One broadcast of AB (the (n, 2l+u+1) factor slab) and one of ipiv from ``src`` (NCCL on GPUs, gloo on CPU
+    tensors in the unit tests).  In place; returns the two tensors."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(data, src, group=group)
+        dist.broadcast(ipiv, src, group=group)
+    return data, ipiv
+
+
+class ShardedSolve:
+    """``ldiv!(F, B)`` with the columns of B sharded over the ranks.
+
+    ``F`` is the BandedLU on rank ``src`` (``None`` elsewhere); ``n, l, u`` describe the ORIGINAL matrix (factors have
+    bandwidths (l, l+u)).  After construction every rank holds a replica of the factors; ``ldiv_(B_local)`` solves
+    this rank's column block in place."""
+
+    def __init__(self, F, n: int, l: int, u: int, rank: int, world: int, group=None, src: int = 0, device=None):
+        from .linalg import BandedLU
+
+        self.rank, self.world, self.n, self.l, self.u = rank, world, n, l, u
+        if F is not None:
+            data, ipiv_d = F.factors.data, F.d_ipiv()
+        else:
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            data = torch.empty((n, 2 * l + u + 1), dtype=torch.float64, device=dev)
+            ipiv_d = torch.empty(n, dtype=torch.int64, device=dev)
+        broadcast_factors(data, ipiv_d, src, group)
+        if F is None:
+            F = BandedLU(BandedMatrix(data, n, l, l + u), ipiv_d.cpu().numpy(), 0, ipiv_d)
+        self.F = F
+
+    def ldiv_(self, B_local: torch.Tensor) -> torch.Tensor:
+        from .linalg import ldiv_
+
+        return ldiv_(self.F, B_local)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# banded x banded, sharded over the COLUMNS of B and C (SURVEY.md 8e; reference _gbmm!, src/banded/gbmm.jl:296-340: column
+# j of C is one gbmv over A's columns [j-Bu, j+Bl]).  Rank r owns columns [j0, j1) of B and C and needs A's columns
+# [j0-Bu, j1+Bl): a STATIC halo, replicated once at distribution time (build_extended_slab) -- no exchange per product.
+# In band storage an off-diagonal sub-block is the same data with re-labelled bandwidths, so the local product is one
+# ordinary bmb200_dgbmm_bb call and every entry sees the same FMAs in the same order as in the unsharded product.
+# ---------------------------------------------------------------------------------------------------------------------
+def gbmm_shard_geometry(n: int, Ab, Bb, j0: int, j1: int):
+    """Sub-problem of C[:, j0:j1] = A * B[:, j0:j1] for square n x n operands with bandwidths Ab=(Al,Au), Bb=(Bl,Bu) and
+    C = (Al+Bl, Au+Bu): the A columns [v0, v1) and rows [r0, r1) it touches and the bandwidths of the three sub-blocks."""
+    (Al, Au), (Bl, Bu) = Ab, Bb
+    Cl, Cu = Al + Bl, Au + Bu
+    v0, v1 = max(0, j0 - Bu), min(n, j1 + Bl)
+    r0, r1 = max(0, j0 - Cu), min(n, j1 + Cl)
+    sa, sb, sc = r0 - v0, v0 - j0, r0 - j0  # row-minus-column origin shift of each sub-block
+    return {"v0": v0, "v1": v1, "r0": r0, "r1": r1, "rows": r1 - r0, "inner": v1 - v0, "cols": j1 - j0,
+            "A": (Al - sa, Au + sa), "B": (Bl - sb, Bu + sb), "C": (Cl - sc, Cu + sc)}
+
+
+class ShardedGbmm:
+    """``mul!(C, A, B, alpha, beta)`` for banded A, B, C with B and C sharded by columns.
+
+    ``A_cols`` holds A's data columns [v0, v1) (tensor layout (v1-v0, Al+Au+1)) -- pass ``A_local`` = columns [j0, j1)
+    plus ``extend=True`` to let the constructor fetch the halo from the neighbours."""
+
+    def __init__(self, n: int, Ab, Bb, j0: int, j1: int, A_cols: torch.Tensor, rank: int = 0, world: int = 1, group=None,
+                 extend: bool = False):
+        self.n, self.Ab, self.Bb, self.j0, self.j1 = n, tuple(Ab), tuple(Bb), j0, j1
+        self.geo = gbmm_shard_geometry(n, Ab, Bb, j0, j1)
+        if extend:
+            A_cols = build_extended_slab(A_cols, n, j0, j1, Bb[1], Bb[0], rank, world, group)  # halo: Bu left, Bl right
+        assert A_cols.shape[0] == self.geo["inner"], "A_cols must hold A's columns [j0-Bu, j1+Bl)"
+        self.A_cols = A_cols
+        g = self.geo
+        if min(g["rows"], g["cols"]) - 1 < max(g["C"]):
+            raise ValueError("slab narrower than the product's bandwidth: use fewer ranks")
+
+    def __call__(self, alpha: float, B_local: torch.Tensor, beta: float, C_local: torch.Tensor) -> torch.Tensor:
+        """B_local: (j1-j0, Bl+Bu+1) band data of B's columns; C_local: (j1-j0, Cl+Cu+1), overwritten."""
+        g = self.geo
+        hd = _lib.handle(C_local.device.index)
+        lda = int(self.A_cols.stride(0))
+        hd.check(hd.lib.bmb200_dgbmm_bb(hd.h, g["rows"], g["inner"], g["cols"], g["A"][0], g["A"][1], g["B"][0], g["B"][1],
+                                        g["C"][0], g["C"][1], float(alpha), vp(self.A_cols.data_ptr()), lda,
+                                        vp(B_local.data_ptr()), int(B_local.stride(0)), float(beta),
+                                        vp(C_local.data_ptr()), int(C_local.stride(0))), "dgbmm_bb (column shard)")
+        return C_local
+
+
+class ShardedGbmmDense:
+    """banded x dense with the RIGHT-HAND-SIDE columns of B and C sharded (src/generic/matmul.jl:243-256: one gbmv per
+    column, so column blocks are independent); A is replicated, no halo and no exchange."""
+
+    def __init__(self, A: BandedMatrix, rank: int = 0, world: int = 1):
+        self.A, self.rank, self.world = A, rank, world
+
+    def __call__(self, alpha: float, B_local: torch.Tensor, beta: float, C_local: torch.Tensor) -> torch.Tensor:
+        from .linalg import mul_
+
+        return mul_(C_local, self.A, B_local, alpha, beta)

@@ -4,7 +4,9 @@
 A "step" = one gbmv  y <- A*x  over the C2 workload: Float64, n = 2^27, (l,u) = (4,3)  [80*n bytes].
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (one rank per GPU under torchrun)
   python bench.py --impl reference ...                        the reference's CPU path (OpenBLAS dgbmv_) on host cores
-Prints ONE JSON line.  See DESIGN.md "Measurement" for what every field means.
+Prints ONE JSON line.  Besides the headline (C2) it carries "configs": the other BASELINE.json configurations (C1, C3, C4,
+C5 -- banded matmul and LU+solve), each timed, set against its roofline and the CPU reference, and verified against OpenBLAS
+at the full benchmark size (bench_configs.py).  See DESIGN.md "Measurement" for what every field means.
 """
 import argparse
 import json
@@ -106,10 +108,14 @@ def run_reference(args):
     if rank != 0:
         return
     L = cpu_driver()
-    n = args.n if args.n else (1 << 25)  # bounded sample of the C2 workload: 2^25 rows (2.7 GB), ~0.4 s per step
+    n = args.n if args.n else N_C2  # the full C2 workload (10.7 GB of host arrays, ~1.5 s per step): same config as our arm
     rng = np.random.default_rng(1)
-    data = np.asfortranarray(rng.random((LDA, n)))
-    x = rng.random(n)
+    blk = 1 << 20  # a random 2^20-column block tiled over the matrix: the values do not matter to dgbmv_'s speed
+    data = np.empty((LDA, n), order="F")
+    tile = np.asfortranarray(rng.random((LDA, min(blk, n))))
+    for j in range(0, n, blk):
+        data[:, j:j + blk] = tile[:, : min(blk, n - j)]
+    x = np.tile(rng.random(min(blk, n)), -(-n // blk))[:n].copy()
     y = np.zeros(n)
     cores = os.cpu_count() or 1
     # OpenBLAS runs dgbmv single-threaded for kl+ku < 15 whatever the thread setting; give it every core anyway
@@ -121,14 +127,24 @@ def run_reference(args):
         t += L.drv_gbmv(n, n, KL, KU, 1.0, data.ctypes.data, LDA, x.ctypes.data, 0.0, y.ctypes.data)
     ms = 1e3 * t / args.steps
     val = algo_bytes(n) / (ms * 1e-3) / 1e9
-    sample = f"n=2^{int(np.log2(n))} rows of the C2 workload per step (OpenBLAS 0.3.30 dgbmv_64_, threads={cores}; narrow-band gbmv is single-threaded inside OpenBLAS)"
+    sample = f"the full C2 workload per step, n=2^{int(np.log2(n))} rows (OpenBLAS 0.3.30 dgbmv_64_, threads={cores}; narrow-band gbmv is single-threaded inside OpenBLAS)"
+    configs = None
+    if args.configs:
+        try:  # the reference's CPU timings of the other BASELINE configs (bounded samples; see bench_configs.py)
+            from bench_extras import cpu_extras
+
+            configs = cpu_extras(L, cores)
+        except Exception as e:  # noqa: BLE001
+            configs = {"error": repr(e)}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 gbmv Float64 (l,u)=(4,3), y=A*x", "n": n, "bytes_per_step": algo_bytes(n)},
+        "config": {"workload": "C2 gbmv Float64 n=2^27 (l,u)=(4,3), y=A*x (alpha=1,beta=0), row-sharded over n_gpus", "n": n,
+                   "bytes_per_step": algo_bytes(n)},
         "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "configs": configs,
     }))
 
 
@@ -222,51 +238,116 @@ def run_ours(args):
                        "n": n, "bytes_per_step": algo_bytes(n), "l2": "inputs (10.7 GB) larger than L2; no flush needed",
                        "parallelism": f"rows/{world}" + (" + x halo over NVLink peer stores" if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "traffic_source": "ncu --set full capture of this command committed as profiles/gbmv_c2_traffic.json (not re-measured in this run)" if traffic else None,
+                         "peak_source": peak_src,
                          "kernel": "gbmv_n_systolic<8,8>", "kernel_ms": round(k_ms, 4), "kernel_ms_min": round(float(np.min(kt)), 4),
                          "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
             "clocks": clocks, "gpu_launches": launches,
         }
 
-    # ---- e2e through the host-buffer C ABI (pinned host arrays, H2D + kernel + D2H inside the timed region) ----
-    # At N > 1 every rank moves its own row slab through its own PCIe link at the same time; the value is the whole-job
-    # aggregate (all rows / max-over-ranks time).  The host-buffer entry point is per slab (no x halo), so this is a
-    # throughput measurement of the same work, not a sharded product.
+    # ---- N > 1: the sharded result checked against OpenBLAS on the rows that straddle EVERY slab boundary ----
+    sharded_check = None
+    if world > 1:
+        Wd = 128  # columns gathered either side of a boundary; rows within 64 of it are compared
+        pack = torch.zeros((2, Wd, LDA + 2), dtype=torch.float64, device="cuda")
+        pack[0, :, :LDA], pack[0, :, LDA], pack[0, :, LDA + 1] = A.data[:Wd], x[:Wd], y[:Wd]
+        pack[1, :, :LDA], pack[1, :, LDA], pack[1, :, LDA + 1] = A.data[nl - Wd:], x[nl - Wd:], y[nl - Wd:]
+        allp = [torch.empty_like(pack) for _ in range(world)]
+        dist.all_gather(allp, pack)
+        if rank == 0 and not args.no_cpu:
+            try:
+                L = cpu_driver()
+                L.drv_set_threads(1)
+                bad, rows = 0, 0
+                for r in range(1, world):
+                    win = torch.cat([allp[r - 1][1], allp[r][0]], dim=0).cpu().numpy()  # 2*Wd columns around the boundary
+                    d_h = np.asfortranarray(win[:, :LDA].T)
+                    x_h, y_gpu = np.ascontiguousarray(win[:, LDA]), win[:, LDA + 1]
+                    y_h = np.zeros(2 * Wd)
+                    L.drv_gbmv(2 * Wd, 2 * Wd, KL, KU, 1.0, d_h.ctypes.data, LDA, x_h.ctypes.data, 0.0, y_h.ctypes.data)
+                    sl = slice(Wd - 64, Wd + 64)  # interior rows of the window: same terms, same order as in the full product
+                    bad += int((y_h[sl] != y_gpu[sl]).sum())
+                    rows += 128
+                sharded_check = {"sharded_bit_identical": bad == 0, "boundary_rows_checked": rows, "mismatches": bad,
+                                 "against": "OpenBLAS dgbmv_64_ on the 256-column windows around every slab boundary"}
+            except Exception as e:  # noqa: BLE001
+                sharded_check = {"sharded_bit_identical": None, "error": repr(e)}
+        op.check()  # raises if a halo wait timed out anywhere in the run
+    if rank == 0 and sharded_check is not None:
+        out["sharded_check"] = sharded_check
+
+    # ---- e2e through the public host-buffer entry points (pinned host arrays, H2D + kernel + D2H inside the timed region).
+    # N = 1: bmb200_dgbmv_host (chunked H2D overlapped with the kernel).  N > 1: the SHARDED product from host buffers --
+    # every rank uploads its extended slab (static data halo included) and its slice of x, the x halo moves between the GPUs
+    # inside the kernel exactly as in the device-resident run, and y comes back to the host; aggregate over ranks. ----
     if not args.no_e2e:
-        ne = n if world == 1 else nl
-        hA = torch.empty((ne, LDA), dtype=torch.float64).pin_memory()
-        hx = torch.empty(ne, dtype=torch.float64).pin_memory()
-        hy = torch.empty(ne, dtype=torch.float64).pin_memory()
-        hA.copy_(A.data)  # device -> pinned host, direct
-        hx.copy_(x)
-        torch.cuda.synchronize()
-        dA_np, x_np, y_np = hA.numpy().T, hx.numpy(), hy.numpy()  # (LDA x n) Fortran view of the same memory
-        bm.gbmv_host("N", ne, KL, KU, 1.0, dA_np, x_np, 0.0, y_np, device=local)  # warm-up (scratch allocation)
         reps = 3
+        if world == 1:
+            hA = torch.empty((n, LDA), dtype=torch.float64).pin_memory()
+            hx = torch.empty(n, dtype=torch.float64).pin_memory()
+            hy = torch.empty(n, dtype=torch.float64).pin_memory()
+            hA.copy_(A.data)  # device -> pinned host, direct
+            hx.copy_(x)
+            torch.cuda.synchronize()
+            dA_np, x_np, y_np = hA.numpy().T, hx.numpy(), hy.numpy()  # (LDA x n) Fortran view of the same memory
+            e2e_step = lambda: bm.gbmv_host("N", n, KL, KU, 1.0, dA_np, x_np, 0.0, y_np, device=local)  # noqa: E731
+            h2d, d2h = 8 * n * (LDA + 1), 8 * n
+            api = "bmb200_dgbmv_host (pinned host arrays)"
+        else:
+            ext = op.data_ext
+            hA = torch.empty(ext.shape, dtype=torch.float64).pin_memory()
+            hx = torch.empty(nl, dtype=torch.float64).pin_memory()
+            hy = torch.empty(nl, dtype=torch.float64).pin_memory()
+            hA.copy_(ext)
+            hx.copy_(x)
+            torch.cuda.synchronize()
+            y2 = torch.empty_like(y)
+
+            def e2e_step():
+                ext.copy_(hA, non_blocking=True)
+                x.copy_(hx, non_blocking=True)
+                op(1.0, x, 0.0, y2)
+                hy.copy_(y2, non_blocking=True)
+                torch.cuda.synchronize()
+
+            h2d, d2h = 8 * (ext.numel() + nl), 8 * nl
+            api = "ShardedGbmv from pinned host buffers (extended slab + x slice up, in-kernel x halo over NVLink, y slice down), all ranks concurrently"
+        e2e_step()  # warm-up (scratch allocation)
         barrier()
         t0 = time.perf_counter()
         for _ in range(reps):
-            bm.gbmv_host("N", ne, KL, KU, 1.0, dA_np, x_np, 0.0, y_np, device=local)
+            e2e_step()
+        if world > 1:
+            barrier()
         dt = (time.perf_counter() - t0) / reps
         if world > 1:
-            td = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-            dt = float(td.item())
-        same = bool(torch.equal(hy.cuda(), y)) if world == 1 else None
+            td = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+            tmax = td[:1].clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(td)
+            dt, h2d, d2h = float(tmax.item()), int(td[1].item()), int(td[2].item())
+            same_t = torch.tensor([1 if torch.equal(hy.cuda(), y) else 0], device="cuda")
+            dist.all_reduce(same_t, op=dist.ReduceOp.MIN)
+            same = bool(same_t.item())
+        else:
+            same = bool(torch.equal(hy.cuda(), y))
     if rank == 0 and not args.no_e2e:
-        out["e2e"] = {"value": round(algo_bytes(n) / dt / 1e9, 2), "unit": UNIT, "h2d_bytes_per_step": 8 * n * (LDA + 1),
-                      "d2h_bytes_per_step": 8 * n, "ms_per_step": round(dt * 1e3, 2),
-                      "api": "bmb200_dgbmv_host (pinned host arrays" + ("" if world == 1 else "; one row slab per rank, concurrently") + ")",
+        out["e2e"] = {"value": round(algo_bytes(n) / dt / 1e9, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "ms_per_step": round(dt * 1e3, 2), "api": api,
                       "matches_device_path": same, "rows": n}
 
         # ---- CPU baseline beside it: OpenBLAS dgbmv_ on the same host arrays, bounded sample ----
         if not args.no_cpu:
             try:
                 L = cpu_driver()
+                ne = n if world == 1 else nl
                 ns = min(ne, 1 << 26)  # 2^26 rows = half of C2: ~0.75 s per call
+                hs = max(0, (hA.shape[0] - ne) if world > 1 else 0)  # rank 0's slab has no left halo
+                dA_s, x_s, y_s = hA.numpy().T[:, :ns], hx.numpy()[:ns], hy.numpy()[:ns]
                 yc = np.zeros(ns)
-                tb = cpu_gbmv_time(L, ns, dA_np[:, :ns], x_np[:ns], yc, threads=1, reps=3)
-                bit_same = bool(np.array_equal(yc[: ns - KU], y_np[: ns - KU]))
+                tb = cpu_gbmv_time(L, ns, dA_s, x_s, yc, threads=1, reps=3)
+                bit_same = bool(np.array_equal(yc[: ns - KU], y_s[: ns - KU]))
                 out["cpu_baseline"] = {"value": round(algo_bytes(ns) / tb / 1e9, 3), "unit": UNIT, "cores": 1, "kind": "reference",
                                        "sample": f"first 2^{int(np.log2(ns))} rows of the same C2 inputs, OpenBLAS 0.3.30 dgbmv_64_ "
                                                  f"(the Fortran entry point the reference ccalls; single-threaded inside OpenBLAS for kl+ku<15; "
@@ -274,15 +355,31 @@ def run_ours(args):
                                        "gpu_result_bit_identical_on_sample": bit_same}
             except Exception as e:  # the baseline is reporting only; never let it kill the bench line
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+        del hA, hx, hy
+    # ---- free the headline's buffers, then the other BASELINE configs (C1, C3, C4, C5), timed and verified ----
+    del A, x, y
+    if world > 1:
+        op.close()
+        del op
+    torch.cuda.empty_cache()
+    if args.configs:
+        from bench_configs import cpu_protos, run_configs
+
+        Lc = None
+        if not args.no_cpu:
+            try:
+                Lc = cpu_protos(cpu_driver())
+            except Exception:  # noqa: BLE001
+                Lc = None
+        cfg = run_configs(bm, Lc, peak, rank, world)
+        if rank == 0:
+            out["configs"] = cfg
+            out["gpu_launches_configs"] = hd.launches - l0 - launches if world == 1 else None
     if rank == 0 and args.extras and world == 1:
         try:
-            from bench_extras import run_extras
+            from bench_extras import run_secondary
 
-            out["extras"] = run_extras(bm)
-            if not args.no_cpu:
-                from bench_extras import cpu_extras
-
-                out["extras"]["cpu_reference"] = cpu_extras(cpu_driver(), os.cpu_count() or 1)
+            out["extras"] = run_secondary(bm)
         except Exception as e:  # noqa: BLE001
             out["extras"] = {"error": repr(e)}
     if rank == 0:
@@ -301,7 +398,9 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the row count (debugging only; the headline is n=2^27)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time C1/C3/C4 (banded matmul, LU+solve) into 'extras'")
+    ap.add_argument("--no-configs", dest="configs", action="store_false",
+                    help="headline only: skip the C1/C3/C4/C5 entries (banded matmul, LU+solve) of 'configs'")
+    ap.add_argument("--extras", action="store_true", help="also time the triangular / symmetric band and elementwise kernels into 'extras'")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,5 +1,6 @@
-"""Secondary configurations of BASELINE.json timed on one GPU (reported under "extras" by bench.py --extras):
-C1 README brand(10000,10000,4,3): A*b, A*A, A\\b;  C3 banded*banded n=2^22 (32,32)^2;  C4 LU+solve n=2^20 (16,16), 256 RHS.
+"""Secondary kernels timed on one GPU (reported under "extras" by bench.py --extras: triangular band tbsv/tbmv, symmetric band
+sbmv, band-aligned axpy), and `cpu_extras`: the reference's CPU timings of the BASELINE configs on bounded samples, which the
+reference arm (bench.py --impl reference) reports under "configs".  The GPU side of C1/C3/C4/C5 lives in bench_configs.py.
 CUDA events on the launching stream, best of `reps` after one warm-up."""
 import numpy as np
 import torch
@@ -19,46 +20,6 @@ def _time(fn, reps=5, setup=None):
         if i:
             best = min(best, a.elapsed_time(b))
     return best
-
-
-def laplacian(bm, N):
-    """examples/finitedifference_2d.jl: A = I - dt*Laplacian_2D, dt = 1/(4 N^2): diag 2, +-1 and +-N bands -0.25."""
-    n = N * N
-    A = bm.BandedMatrix.zeros((n, n), (N, N))
-    d = A.data  # (n, 2N+1): d[j, r] = band row r of column j
-    d[:, N] = 2.0
-    j = torch.arange(n, device=d.device)
-    d[1:, N - 1] = torch.where(j[1:] % N != 0, -0.25, 0.0).to(d.dtype)
-    d[:-1, N + 1] = torch.where((j[:-1] + 1) % N != 0, -0.25, 0.0).to(d.dtype)
-    d[N:, 0] = -0.25
-    d[:-N, 2 * N] = -0.25
-    return A
-
-
-def run_c5(bm, N=1024):
-    n = N * N
-    A = laplacian(bm, N)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    F = bm.lu(A)
-    b.record()
-    b.synchronize()
-    t_f = a.elapsed_time(b)
-    rhs = torch.ones(n, dtype=torch.float64, device="cuda")
-    x = rhs.clone()
-    a.record()
-    bm.ldiv_(F, x)
-    b.record()
-    b.synchronize()
-    t_s = a.elapsed_time(b)
-    r = rhs.clone()
-    bm.mul_(r, A, x, -1.0, 1.0)
-    res = float(r.abs().max() / x.abs().max())
-    ident = bool((torch.as_tensor(F.ipiv) == torch.arange(1, n + 1)).all())
-    flops = 2.0 * n * N * N + n * N
-    return {"N": N, "n": n, "lu_ms_incl_widen": round(t_f, 1), "lu_TFLOPs": round(flops / t_f / 1e9, 3), "solve_ms": round(t_s, 1),
-            "pivots_identity": ident, "max_residual_over_max_x": res}
 
 
 def cpu_extras(L, cores):
@@ -148,60 +109,11 @@ def cpu_extras(L, cores):
     return out
 
 
-def run_extras(bm, c3_n=1 << 22, c4_n=1 << 20, c4_rhs=256):
+def run_secondary(bm):
+    """Secondary kernels: triangular band solve / multiply, symmetric band matvec, band-aligned axpy."""
+    from bench_configs import laplacian
+
     out = {}
-    # ---- C1 ----
-    n = 10000
-    A = bm.brand(n, n, 4, 3, seed=1)
-    b = torch.randn(n, dtype=torch.float64, device="cuda")
-    y = torch.empty_like(b)
-    C = bm.BandedMatrix.undef((n, n), (8, 6))
-    out["C1_Ab_us"] = round(1e3 * _time(lambda: bm.mul_(y, A, b)), 2)
-    out["C1_AA_us"] = round(1e3 * _time(lambda: bm.mul_(C, A, A)), 2)
-    out["C1_solve_us"] = round(1e3 * _time(lambda: bm.solve(A, b)), 2)
-    # ---- C3 ----
-    n = c3_n
-    A = bm.brand(n, n, 32, 32, seed=2)
-    B = bm.brand(n, n, 32, 32, seed=3)
-    C = bm.BandedMatrix.undef((n, n), (64, 64))
-    ms = _time(lambda: bm.mul_(C, A, B), reps=3)
-    flops = 2.0 * 65 * 65 * n
-    byts = 8.0 * n * (65 + 65 + 129)
-    out["C3"] = {"n": n, "ms": round(ms, 3), "GFLOPs": round(flops / ms / 1e6, 1), "GBs": round(byts / ms / 1e6, 1),
-                 "hbm_roofline_ms": round(byts / 6531.9e6, 3)}
-    del A, B, C
-    # ---- C4 ----
-    n, l, u, nrhs = c4_n, 16, 16, c4_rhs
-    A = bm.brand(n, n, l, u, seed=4)
-    W = bm.BandedMatrix.undef((n, n), (l, 2 * l + u - l))
-    keep = {}
-
-    def widen():
-        hd = bm.handle(0)
-        import ctypes as Ct
-        hd.check(hd.lib.bmb200_dband_widen(hd.h, n, l, u, Ct.c_void_p(A.ptr), A.lda, Ct.c_void_p(W.ptr), W.lda), "widen")
-
-    def factor():
-        keep["F"] = bm.lu_(W)
-
-    t_f = _time(factor, reps=2, setup=widen)
-    F = keep["F"]
-    nontrivial = int((F.ipiv != np.arange(1, n + 1)).sum())
-    X = bm.colmajor(n, nrhs)
-    Bm = torch.rand((nrhs, n), dtype=torch.float64, device="cuda").T
-
-    def reset():
-        X.copy_(Bm)
-
-    t_s = _time(lambda: bm.ldiv_(F, X), reps=2, setup=reset)
-    fl_s = nrhs * n * (2.0 * l + 2.0 * (l + u) + 1)
-    by_s = 2 * 8.0 * n * nrhs + 8.0 * (2 * l + u + 1) * n + 8.0 * n
-    out["C4"] = {"n": n, "nrhs": nrhs, "gbtrf_ms": round(t_f, 2), "gbtrf_ns_per_column": round(1e6 * t_f / n, 1),
-                 "nontrivial_pivots": nontrivial, "gbtrs_ms": round(t_s, 2), "gbtrs_GFLOPs": round(fl_s / t_s / 1e6, 1),
-                 "gbtrs_GBs": round(by_s / t_s / 1e6, 1), "gbtrs_hbm_roofline_ms": round(by_s / 6531.9e6, 3)}
-    del F, X, Bm, W, A
-    torch.cuda.empty_cache()
-    out["C5"] = run_c5(bm, 1024)
     # ---- triangular band (SURVEY 8f rank 2): the Gauss-Seidel half of examples/finitedifference_2d.jl:18-26 at C5 size ----
     N = 1024
     A = laplacian(bm, N)

@@ -13,7 +13,78 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
-from bandedmatrices_b200.sharded import build_extended_slab, shard_bounds, slab_geometry  # noqa: E402
+from bandedmatrices_b200.sharded import (broadcast_factors, build_extended_slab, gbmm_shard_geometry, rhs_bounds,  # noqa: E402
+                                         shard_bounds, slab_geometry)
+
+
+def check_sharded_solve(backend, rank, world, C):
+    """RHS-sharded ldiv! (SURVEY.md 8e): factor on rank 0, broadcast AB + ipiv, every rank solves its block of columns;
+    the blocks together must be the oracle's DGBTRS solution bit for bit."""
+    n, l, u, nrhs = 3000, 5, 4, 7 * world + 3
+    rng = np.random.default_rng(11)
+    A = oracle.brand(rng, n, n, l, u)
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    ab, ipiv, info = oracle.lu(C, A)
+    ref = B.copy(order="F")
+    oracle.ldiv(C, "N", ab, ipiv, l, u, ref)
+    q0, q1 = rhs_bounds(nrhs, rank, world)
+    owned = [rhs_bounds(nrhs, r, world) for r in range(world)]
+    assert owned[0][0] == 0 and owned[-1][1] == nrhs and all(owned[i][1] == owned[i + 1][0] for i in range(world - 1))
+    if backend == "gloo":
+        # plumbing: only rank 0 holds the factors before the broadcast
+        data = torch.as_tensor(np.ascontiguousarray(ab.T)) if rank == 0 else torch.zeros((n, 2 * l + u + 1), dtype=torch.float64)
+        piv = torch.as_tensor(ipiv.astype(np.int64)) if rank == 0 else torch.zeros(n, dtype=torch.int64)
+        broadcast_factors(data, piv, 0)
+        assert np.array_equal(data.numpy().T, ab) and np.array_equal(piv.numpy(), ipiv)
+        Xl = np.asfortranarray(B[:, q0:q1].copy())
+        oracle.ldiv(C, "N", np.asfortranarray(data.numpy().T), piv.numpy(), l, u, Xl)
+        assert np.array_equal(Xl, ref[:, q0:q1])
+    else:
+        import bandedmatrices_b200 as bm
+        from bandedmatrices_b200.sharded import ShardedSolve
+
+        F = bm.lu(bm.BandedMatrix.from_banddata(A.data, n, l, u)) if rank == 0 else None
+        S = ShardedSolve(F, n, l, u, rank, world)
+        assert np.array_equal(S.F.ipiv, ipiv)
+        Xl = bm.to_colmajor(B[:, q0:q1])
+        S.ldiv_(Xl)
+        assert np.array_equal(Xl.cpu().numpy(), ref[:, q0:q1]), ("sharded solve", rank)
+
+
+def check_sharded_gbmm(backend, rank, world, C):
+    """Column-sharded banded x banded: every rank's slab of C equals the same columns of the unsharded _gbmm! result."""
+    for (n, Ab, Bb) in [(1500, (3, 2), (4, 1)), (2000, (9, 12), (10, 9)), (4096, (32, 32), (32, 32))]:
+        rng = np.random.default_rng(13)
+        A = oracle.brand(rng, n, n, *Ab)
+        B = oracle.brand(rng, n, n, *Bb)
+        Cl, Cu = Ab[0] + Bb[0], Ab[1] + Bb[1]
+        ref = np.zeros((Cl + Cu + 1, n), order="F")
+        oracle.gbmm_kernel(C, 1.0, A.data, B.data, 0.0, ref, n, n, n, Ab[0], Ab[1], Bb[0], Bb[1], Cl, Cu)
+        j0, j1 = shard_bounds(n, rank, world)
+        g = gbmm_shard_geometry(n, Ab, Bb, j0, j1)
+        assert g["A"][0] + g["A"][1] == sum(Ab) and g["B"][0] + g["B"][1] == sum(Bb) and g["C"][0] + g["C"][1] == Cl + Cu
+        assert min(g["A"] + g["B"] + g["C"]) >= 0
+        dev = "cuda" if backend == "nccl" else "cpu"
+        A_local = torch.as_tensor(np.ascontiguousarray(A.data.T[j0:j1])).to(dev)
+        A_cols = build_extended_slab(A_local, n, j0, j1, Bb[1], Bb[0], rank, world)
+        assert np.array_equal(A_cols.cpu().numpy(), A.data.T[g["v0"]:g["v1"]])
+        # in-matrix entries of the slab's columns
+        rr, jj = np.meshgrid(np.arange(Cl + Cu + 1), np.arange(j0, j1), indexing="ij")
+        inm = (jj + rr - Cu >= 0) & (jj + rr - Cu < n)
+        if backend == "gloo":
+            sub = np.zeros((Cl + Cu + 1, j1 - j0), order="F")
+            oracle.gbmm_kernel(C, 1.0, np.asfortranarray(A_cols.numpy().T), np.asfortranarray(B.data[:, j0:j1]), 0.0, sub, g["rows"],
+                               g["inner"], g["cols"], g["A"][0], g["A"][1], g["B"][0], g["B"][1], g["C"][0], g["C"][1])
+            assert np.array_equal(sub[inm], ref[:, j0:j1][inm]), ("gbmm slab", n, rank)
+        else:
+            from bandedmatrices_b200.sharded import ShardedGbmm
+
+            op = ShardedGbmm(n, Ab, Bb, j0, j1, A_local, rank, world, extend=True)
+            B_local = torch.as_tensor(np.ascontiguousarray(B.data.T[j0:j1])).cuda()
+            C_local = torch.full((j1 - j0, Cl + Cu + 1), float("nan"), dtype=torch.float64, device="cuda")
+            op(1.0, B_local, 0.0, C_local)
+            torch.cuda.synchronize()
+            assert np.array_equal(C_local.cpu().numpy().T[inm], ref[:, j0:j1][inm]), ("gbmm slab", n, rank)
 
 
 def main():
@@ -62,6 +133,8 @@ def main():
                 assert np.array_equal(yl.cpu().numpy(), ref[c0:c1]), (n, kl, ku, rank, it)
         if backend == "nccl":
             op.close()
+    check_sharded_solve(backend, rank, world, C)
+    check_sharded_gbmm(backend, rank, world, C)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

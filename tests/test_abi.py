@@ -6,8 +6,8 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    src = open(os.path.join(ROOT, "include", "bmb200.h")).read()
+def _declared(header="bmb200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(bmb200_[a-z0-9_]+)\s*\(", src)))
 
@@ -22,6 +22,12 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in include/bmb200.h but not exported by libbmb200.so"
     assert set(names) == set(bm.PROTOTYPES), "ctypes prototypes drifted from include/bmb200.h"
     assert bm.load().bmb200_version() == 100
+    from bandedmatrices_b200 import _lib
+
+    internal = _declared("bmb200_internal.h")
+    for name in internal:
+        assert hasattr(lib, name), f"{name} declared in include/bmb200_internal.h but not exported"
+    assert set(internal) == set(_lib.INTERNAL_PROTOTYPES)
 
 
 def test_no_cpu_fallback_without_gpu():

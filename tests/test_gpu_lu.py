@@ -281,8 +281,6 @@ def test_blocked_solve_fast_division_is_the_ieee_quotient(bm, rng):
 
     hd = bm.handle(0)
     fn = hd.lib.bmb200_internal_divcheck
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     n = 1 << 24
     m = rng.random(n) + 1.0
     e = rng.integers(-1000, 1000, n)
@@ -303,3 +301,66 @@ def test_blocked_solve_fast_division_is_the_ieee_quotient(bm, rng):
     hd.check(fn(hd.h, n, C.c_void_p(dx.data_ptr()), C.c_void_p(dd.data_ptr()), C.c_void_p(bad.data_ptr())), "divcheck")
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+    # the slot-scheduled solve's division (gbtrs_slot.cu): q = fma(t, r_hi, t*r_lo) accepted only when one Markstein
+    # correction reproduces it, IEEE division otherwise -- the accepted value must be the IEEE quotient on every input,
+    # and nearly all ordinary operands must take the verified fast path
+    bad2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+    hd.check(hd.lib.bmb200_internal_divcheck2(hd.h, n, C.c_void_p(dx.data_ptr()), C.c_void_p(dd.data_ptr()),
+                                              C.c_void_p(bad2.data_ptr())), "divcheck2")
+    torch.cuda.synchronize()
+    assert int(bad2[0].item()) == 0
+    assert int(bad2[1].item()) > 0.2 * n  # an operand beyond 2^+-500 (3/4 of this sample) takes the IEEE route
+
+
+@pytest.mark.parametrize("PF,PB,W", [(2, 2, 1), (4, 2, 2), (4, 4, 1), (4, 4, 4), (4, 8, 8), (8, 4, 2), (8, 8, 4)])
+@pytest.mark.parametrize("shape", [(1000, 16, 16, 5), (777, 4, 3, 9), (64, 3, 2, 2), (3000, 24, 8, 3), (130, 5, 7, 17),
+                                   (1, 0, 0, 1), (5, 4, 4, 1), (2000, 0, 3, 2), (2000, 3, 0, 2), (4097, 1, 1, 4),
+                                   (63, 2, 30, 1), (65, 20, 12, 33)])
+def test_slot_scheduled_solve_bit_identical(bm, oracle_c, rng, shape, PF, PB, W):
+    """gbtrs_slot.cu, every (PF, PB, W) variant through the internal hook: solutions bit-identical to DGBTRS 'N' with
+    interchanges, ragged n around the 64-column schedule stages, kl = 0, ku = 0, more RHS than a CTA holds."""
+    import ctypes as C
+
+    n, l, u, nrhs = shape
+    if l + PF > 32:
+        pytest.skip("window does not fit a warp for this P")
+    A = brand(rng, n, n, l, u)
+    ab, ipiv, info = lu(oracle_c, A)
+    B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    B[rng.integers(0, n, 3), 0] = 0.0  # exact zeros take the verified-division fallback
+    ref = B.copy(order="F")
+    ldiv(oracle_c, "N", ab, ipiv, l, u, ref)
+    hd = bm.handle(0)
+    dab = torch.as_tensor(np.ascontiguousarray(ab.T)).cuda()  # (n, ldab): column j of AB contiguous
+    dip = torch.as_tensor(ipiv.astype(np.int64)).cuda()
+    X = bm.to_colmajor(B)
+    rc = hd.lib.bmb200_internal_gbtrs_slot(hd.h, PF, PB, W, n, l, u, nrhs, C.c_void_p(dab.data_ptr()), ab.shape[0],
+                                           C.c_void_p(dip.data_ptr()), C.c_void_p(X.data_ptr()), max(1, n))
+    hd.check(rc, "internal_gbtrs_slot")
+    torch.cuda.synchronize()
+    assert np.array_equal(X.cpu().numpy(), ref, equal_nan=True)
+
+
+def test_slot_solve_sparse_rhs_and_nonfinite(bm, oracle_c, rng):
+    """Unit-vector right-hand sides (long runs of exact zeros: the fast division's zero route), and an Inf / NaN planted
+    in b: both must propagate exactly as in DGBTRS (absent updates never touch a row before it enters the window)."""
+    n, l, u = 500, 6, 5
+    A = brand(rng, n, n, l, u)
+    ab, ipiv, info = lu(oracle_c, A)
+    B = np.zeros((n, 6), order="F")
+    B[0, 0] = 1.0
+    B[n - 1, 1] = -2.0
+    B[250, 2] = 3.0
+    B[:, 3] = rng.standard_normal(n)
+    B[300, 3] = np.inf
+    B[:, 4] = rng.standard_normal(n)
+    B[100, 4] = np.nan
+    B[:, 5] = -0.0
+    ref = B.copy(order="F")
+    ldiv(oracle_c, "N", ab, ipiv, l, u, ref)
+    F = bm.BandedLU(bm.BandedMatrix.from_banddata(ab, n, l, l + u), ipiv, 0)
+    X = bm.to_colmajor(B)
+    bm.ldiv_(F, X)
+    got = X.cpu().numpy()
+    assert np.array_equal(got, ref, equal_nan=True)
+    assert np.array_equal(np.signbit(got[:, 5]), np.signbit(ref[:, 5]))  # signed zeros survive too
