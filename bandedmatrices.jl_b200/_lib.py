@@ -51,7 +51,7 @@ INTERNAL_PROTOTYPES = {
     "bmb200_internal_divcheck": (C.c_int, [vp, i64, vp, vp, vp]),
     "bmb200_internal_divcheck2": (C.c_int, [vp, i64, vp, vp, vp]),
     "bmb200_internal_set_tuning": (C.c_int, [vp, C.c_char_p, C.c_longlong]),
-    "bmb200_internal_gbtrs_slot": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, i64, i64, i64, i64, vp, i64, vp, vp, i64]),
+    "bmb200_internal_gbtrs_slot": (C.c_int, [vp] + [C.c_int] * 5 + [i64, i64, i64, i64, vp, i64, vp, vp, i64]),
 }
 
 _lib = None

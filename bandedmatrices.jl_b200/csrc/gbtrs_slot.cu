@@ -400,7 +400,9 @@ __device__ __forceinline__ void sl_triangle(const double (&v)[P], double (&xs)[P
     }
 }
 
-template <int P, bool BWD, int W>
+// R right-hand sides per warp: R independent dependency chains share one instruction stream (and one copy of every
+// schedule word), so the issue slots one chain leaves empty while it waits on its own DFMA are taken by the other.
+template <int P, bool BWD, int W, int R>
 __global__ void __launch_bounds__((W + 1) * 32, 1)
 gbtrs_slot(i64 n, int kl, i64 nrhs, const unsigned char *__restrict__ sched, int nstages, double *__restrict__ b, i64 ldb)
 {
@@ -409,10 +411,11 @@ gbtrs_slot(i64 n, int kl, i64 nrhs, const unsigned char *__restrict__ sched, int
     unsigned char *sring = smem;                                                              // SL_NS stages
     unsigned long long *full = reinterpret_cast<unsigned long long *>(sring + SL_NS * F::STAGE);  // [SL_NS]
     unsigned long long *empty = full + SL_NS;                                                 // [SL_NS]
-    double *bring_all = reinterpret_cast<double *>(empty + SL_NS);                            // W x SL_RB (+ slack for the
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                               //  last stage's src look-ahead)
-    const i64 r0 = (i64)blockIdx.x * W;
-    const int nact = (int)((nrhs - r0 < W) ? (nrhs - r0) : W);
+    double *bring_all = reinterpret_cast<double *>(empty + SL_NS);                            // W*R x SL_RB, then W*R pivot buffers
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 q0 = (i64)blockIdx.x * (W * R);                                                 // first right-hand side of this CTA
+    const i64 left = nrhs - q0;
+    const int nact = (int)((left < W * R) ? (left + R - 1) / R : W);                          // warps with at least one right-hand side
     if (threadIdx.x == 0) {
         for (int s = 0; s < SL_NS; ++s) {
             sl_mbar_init(&full[s], 1);
@@ -435,29 +438,41 @@ gbtrs_slot(i64 n, int kl, i64 nrhs, const unsigned char *__restrict__ sched, int
     }
     if (warp >= nact) return;
 
-    double *bring = bring_all + warp * SL_RB;
-    const unsigned bring_s = sl_smem(bring);
     const unsigned sring_s = sl_smem(sring);
-    double *bcol = b + (r0 + warp) * ldb;
     auto rowof = [&](i64 v) -> i64 { return BWD ? n - 1 - v : v; };
-    for (int c = 0; c < SL_LA / 32; ++c) {
-        const i64 v = 32 * c + lane;
-        if (v < n) sl_cp8(bring + v, bcol + rowof(v));
+    double *bring[R];
+    unsigned bring_s[R], pbuf_s[R], xprev_s[R];
+    double *bcol[R];
+    bool live[R];  // a warp's trailing right-hand sides past nrhs shadow its first one (same arithmetic, nothing stored)
+    double w[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const i64 q = q0 + (i64)warp * R + r;
+        live[r] = q < nrhs;
+        bcol[r] = b + (live[r] ? q : q0 + (i64)warp * R) * ldb;
+        bring[r] = bring_all + (size_t)(warp * R + r) * SL_RB;
+        bring_s[r] = sl_smem(bring[r]);
+        // pivot exchange buffer: the lane that holds the pivot row of step c stores it to pbuf[2+c], everyone reads all P
+        // back with broadcast LDS.128 (1 + P/2 shared-memory operations instead of 2P shuffles); pbuf[1] is a dummy
+        pbuf_s[r] = sl_smem(bring_all + (size_t)W * R * SL_RB) + (unsigned)(warp * R + r) * (8u * P + 16u);
+        xprev_s[r] = bring_s[r] + 8u * (SL_RB - P);  // ring address of the previous block's solution entries
+        for (int c = 0; c < SL_LA / 32; ++c) {
+            const i64 v = 32 * c + lane;
+            if (v < n) sl_cp8(bring[r] + v, bcol[r] + rowof(v));
+        }
     }
     sl_commit();
     sl_wait<0>();
     __syncwarp();
-    double w = 0.0;
-    if ((BWD || lane < kl + P) && lane < n) w = bring[lane];
-    // pivot exchange buffer of this warp: the lane that holds the pivot row of step c stores it to pbuf[c], everyone reads
-    // all P back with broadcast LDS.128 (1 + P/2 shared-memory operations instead of 2P shuffles)
-    const unsigned pbuf_s = sl_smem(bring_all + (size_t)W * SL_RB) + (unsigned)warp * (8u * P + 16u);  // [dummy, pad, P pivots]
-    int slot = 0;
-    unsigned phase = 0, vbr8 = 0;            // vbr8 = ring byte offset of the current block's first row
-    unsigned xprev_s = bring_s + 8u * (SL_RB - P);  // ring address of the previous block's solution entries (lane 0 stores them)
-    double xsp[P];                // the previous block's solution entries: stored behind the next block's pivot exchange
 #pragma unroll
-    for (int c = 0; c < P; ++c) xsp[c] = 0.0;
+    for (int r = 0; r < R; ++r) w[r] = ((BWD || lane < kl + P) && lane < n) ? bring[r][lane] : 0.0;
+    int slot = 0;
+    unsigned phase = 0, vbr8 = 0;  // vbr8 = ring byte offset of the current block's first row
+    double xsp[R][P];              // the previous block's solution entries: stored behind the next block's pivot exchange
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < P; ++c) xsp[r][c] = 0.0;
     unsigned code = 0;
     bool tfull = false;
 #pragma unroll 1
@@ -472,73 +487,101 @@ gbtrs_slot(i64 n, int kl, i64 nrhs, const unsigned char *__restrict__ sched, int
             {   // ---- B ring: prefetch rows [vb+LA, vb+LA+32), retire rows [vb-64, vb-32) ----
                 const i64 vb = (i64)s * SL_COLS + half * 32;
                 const i64 vl = vb + SL_LA + lane;
-                if (vl < n) sl_cp8(bring + (int)(vl & (SL_RB - 1)), bcol + rowof(vl));
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (vl < n) sl_cp8(bring[r] + (int)(vl & (SL_RB - 1)), bcol[r] + rowof(vl));
                 sl_commit();
                 sl_wait<SL_LA / 32 - 2>();
                 __syncwarp();
                 const i64 vs = vb - 64 + lane;
-                if (vb >= 64 && vs < n) bcol[rowof(vs)] = bring[(int)(vs & (SL_RB - 1))];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (vb >= 64 && vs < n && live[r]) bcol[r][rowof(vs)] = bring[r][(int)(vs & (SL_RB - 1))];
             }
 #pragma unroll 1
             for (int g8 = 0; g8 < 32 / P; ++g8) {
                 {   // pivot exchange
                     const unsigned pi8 = __byte_perm(code, 0u, 0x4441);  // byte 1 of code: 8 * (step + 1), 0 = not a pivot lane
                     __syncwarp();
-                    sl_sts64(pbuf_s + 8u + pi8, w);  // pivot c -> pbuf[2 + c]; pbuf[1] is a dummy that the non-pivot lanes hit
+#pragma unroll
+                    for (int r = 0; r < R; ++r) sl_sts64(pbuf_s[r] + 8u + pi8, w[r]);
                     __syncwarp();
                 }
-                double v[P];
+                double v[R][P];
 #pragma unroll
-                for (int c = 0; c < P; c += 2) {
-                    const double2 p2 = sl_lds128(pbuf_s + 16u + 8u * c);
-                    v[c] = p2.x, v[c + 1] = p2.y;
-                }
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < P; c += 2) {
+                        const double2 p2 = sl_lds128(pbuf_s[r] + 16u + 8u * c);
+                        v[r][c] = p2.x, v[r][c + 1] = p2.y;
+                    }
                 // ---- the triangle's multipliers, then the P steps; everything the chain does not need is issued behind them ----
-                SlotRegs<P, BWD> r;
-                sl_fetch<P, BWD>(r, a);
-                double xs[P];
-                if (tfull) sl_triangle<P, BWD, false>(v, xs, r);
-                else sl_triangle<P, BWD, true>(v, xs, r);
+                SlotRegs<P, BWD> sr;
+                sl_fetch<P, BWD>(sr, a);
+                double xs[R][P];
+                if (tfull) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) sl_triangle<P, BWD, false>(v[r], xs[r], sr);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) sl_triangle<P, BWD, true>(v[r], xs[r], sr);
+                }
                 double2 m[P / 2];
 #pragma unroll
                 for (int c2 = 0; c2 < P / 2; ++c2) m[c2] = sl_lds128(a + F::OFF_M + 16u * (c2 * 32 + lane));
                 // the row that enters through this lane (a pivot lane of this block: its old value went into pbuf above)
-                if ((int)code < 0) w = sl_lds64(bring_s + (code >> 16 & 0xfffu));
+                if ((int)code < 0) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) w[r] = sl_lds64(bring_s[r] + (code >> 16 & 0xfffu));
+                }
                 const unsigned code_next = sl_lds32(a + F::BLK + F::OFF_CODE + 4u * lane);  // (past the stage for its last block: replaced)
                 const unsigned tm_next = sl_lds32(a + F::BLK + F::OFF_TM);
 #pragma unroll
-                for (int c = 0; c < P; c += 2) sl_sts128(xprev_s + 8u * c, xsp[c], xsp[c + 1]);  // every lane holds the same values
+                for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int c2 = 0; c2 < P / 2; ++c2) {
-                    sl_fma_if(w, xs[2 * c2], m[c2].x, code & (1u << (2 * c2)));
-                    sl_fma_if(w, xs[2 * c2 + 1], m[c2].y, code & (2u << (2 * c2)));
+                    for (int c = 0; c < P; c += 2) sl_sts128(xprev_s[r] + 8u * c, xsp[r][c], xsp[r][c + 1]);  // every lane holds the same values
+#pragma unroll
+                for (int c2 = 0; c2 < P / 2; ++c2)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        sl_fma_if(w[r], xs[r][2 * c2], m[c2].x, code & (1u << (2 * c2)));
+                        sl_fma_if(w[r], xs[r][2 * c2 + 1], m[c2].y, code & (2u << (2 * c2)));
+                    }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int c = 0; c < P; ++c) xsp[r][c] = xs[r][c];
+                    xprev_s[r] = bring_s[r] + vbr8;
                 }
-#pragma unroll
-                for (int c = 0; c < P; ++c) xsp[c] = xs[c];
                 code = code_next;
                 tfull = tm_next == F::TFULL;
                 a += F::BLK;
-                xprev_s = bring_s + vbr8;
                 vbr8 = (vbr8 + 8u * P) & (8u * SL_RB - 1);
             }
         }
         // ---- end of a schedule stage: renormalise the slots (forward), hand the stage back ----
         if (!BWD) {
             const int em = (int)(sl_lds32(sp_s + F::OFF_END + (lane & ~3u)) >> (8 * (lane & 3))) & 31;
-            w = __shfl_sync(SL_FULL, w, em);
+#pragma unroll
+            for (int r = 0; r < R; ++r) w[r] = __shfl_sync(SL_FULL, w[r], em);
         }
         __syncwarp();
         if (lane == 0) sl_mbar_arrive(&empty[slot]);
         if (++slot == SL_NS) { slot = 0; phase ^= 1u; }
     }
 #pragma unroll
-    for (int c = 0; c < P; c += 2) sl_sts128(xprev_s + 8u * c, xsp[c], xsp[c + 1]);  // the last block's solution entries
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < P; c += 2) sl_sts128(xprev_s[r] + 8u * c, xsp[r][c], xsp[r][c + 1]);  // the last block's solution entries
     // ---- flush the finished rows the in-loop stores have not reached ----
     __syncwarp();
     {
         i64 v0 = (i64)nstages * SL_COLS - 128;
         if (v0 < 0) v0 = 0;
-        for (i64 v = v0 + lane; v < n; v += 32) bcol[rowof(v)] = bring[(int)(v & (SL_RB - 1))];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (live[r])
+                for (i64 v = v0 + lane; v < n; v += 32) bcol[r][rowof(v)] = bring[r][(int)(v & (SL_RB - 1))];
     }
 }
 
@@ -549,21 +592,23 @@ static size_t slot_sched_bytes(i64 n)
     return (size_t)nstages * SlotFmt<P>::STAGE;
 }
 
-template <int P, bool BWD, int W>
+template <int P, bool BWD, int W, int R>
 static int launch_slot_sweep(bmb200_ctx *h, i64 n, int kl, i64 nrhs, const unsigned char *sched, double *dB, i64 ldb)
 {
     using F = SlotFmt<P>;
     const i64 nstages = cdiv64(n, SL_COLS);
     if (nstages >= ((i64)1 << 31)) return 1;
-    const size_t smem = (size_t)SL_NS * F::STAGE + 2 * SL_NS * sizeof(unsigned long long) + (size_t)W * SL_RB * sizeof(double) + (size_t)W * (8 * P + 16) + 64;
-    BMB_CUDA(h, cudaFuncSetAttribute(gbtrs_slot<P, BWD, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)cdiv64(nrhs, W);
-    gbtrs_slot<P, BWD, W><<<blocks, (W + 1) * 32, smem, h->stream>>>(n, kl, nrhs, sched, (int)nstages, dB, ldb);
+    const size_t smem = (size_t)SL_NS * F::STAGE + 2 * SL_NS * sizeof(unsigned long long) +
+                        (size_t)W * R * (SL_RB * sizeof(double) + 8 * P + 16) + 64;
+    BMB_CUDA(h, cudaFuncSetAttribute(gbtrs_slot<P, BWD, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)cdiv64(nrhs, W * R);
+    gbtrs_slot<P, BWD, W, R><<<blocks, (W + 1) * 32, smem, h->stream>>>(n, kl, nrhs, sched, (int)nstages, dB, ldb);
     BMB_LAUNCH_CHECK(h);
     return 0;
 }
 
-template <int PF, int PB, int W>
+// PF / PB: steps per round of the forward / backward sweep; W warps per CTA; RF / RB right-hand sides per warp
+template <int PF, int PB, int W, int RF, int RB>
 static int run_slot(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB,
                     i64 ldb)
 {
@@ -575,24 +620,23 @@ static int run_slot(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double
     if (kl > 0) {
         slot_build_fwd<PF><<<(unsigned)cdiv64(nstages, 4), 128, 0, h->stream>>>(n, (int)kl, (int)kv, dAB, ldab, d_ipiv, sched, nstages);
         BMB_LAUNCH_CHECK(h);
-        if (int rc = launch_slot_sweep<PF, false, W>(h, n, (int)kl, nrhs, sched, dB, ldb)) return rc;
+        if (int rc = launch_slot_sweep<PF, false, W, RF>(h, n, (int)kl, nrhs, sched, dB, ldb)) return rc;
     }
     const i64 nblocks = nstages * SlotFmt<PB>::G;
     const i64 grid = imin64(cdiv64(nblocks, 4), (i64)h->sm_count * 16);
     slot_build_bwd<PB><<<(unsigned)grid, 128, 0, h->stream>>>(n, (int)kv, dAB, ldab, sched, nblocks);
     BMB_LAUNCH_CHECK(h);
-    return launch_slot_sweep<PB, true, W>(h, n, (int)kl, nrhs, sched, dB, ldb);
+    return launch_slot_sweep<PB, true, W, RB>(h, n, (int)kl, nrhs, sched, dB, ldb);
 }
 
-template <int PF, int PB>
+template <int PF, int PB, int RF, int RB>
 static int run_slot_w(bmb200_ctx *h, int W, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
                       double *dB, i64 ldb)
 {
     switch (W) {
-    case 1: return run_slot<PF, PB, 1>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    case 2: return run_slot<PF, PB, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    case 4: return run_slot<PF, PB, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    default: return run_slot<PF, PB, 8>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    case 1: return run_slot<PF, PB, 1, RF, RB>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    case 2: return run_slot<PF, PB, 2, RF, RB>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    default: return run_slot<PF, PB, 4, RF, RB>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
     }
 }
 
@@ -605,28 +649,37 @@ int bmb_gbtrs_slot(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double 
                    i64 ldb)
 {
     if (!slot_covers(4, n, kl, ku)) return 1;
-    // warps (= right-hand sides) per CTA: keep one warp per SM sub-partition while the right-hand sides fit the chip
     const i64 sms = h->sm_count;
-    const int W = (nrhs <= sms) ? 1 : (nrhs <= 2 * sms) ? 2 : (nrhs <= 4 * sms) ? 4 : 8;
-    return run_slot_w<4, 8>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    // few right-hand sides: one per warp, one warp per SM sub-partition; many: two per warp (interleaved chains)
+    if (nrhs <= sms) return run_slot_w<4, 8, 1, 1>(h, 1, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    const i64 warps = cdiv64(nrhs, 2);
+    const int W = (warps <= sms) ? 1 : (warps <= 2 * sms) ? 2 : 4;
+    return run_slot_w<4, 4, 2, 2>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
 }
 
-// ---- development hook (include/bmb200_internal.h): explicit (PF, PB, W) for A/B timing; not part of the public ABI ----
-extern "C" int bmb200_internal_gbtrs_slot(bmb200_handle_t h, int PF, int PB, int W, int64_t n, int64_t kl, int64_t ku,
-                                          int64_t nrhs, const double *dAB, int64_t ldab, const int64_t *d_ipiv, double *dB,
-                                          int64_t ldb)
+// ---- development hook (include/bmb200_internal.h): explicit variant for A/B timing; not part of the public ABI ----
+extern "C" int bmb200_internal_gbtrs_slot(bmb200_handle_t h, int PF, int PB, int W, int RF, int RB, int64_t n, int64_t kl,
+                                          int64_t ku, int64_t nrhs, const double *dAB, int64_t ldab, const int64_t *d_ipiv,
+                                          double *dB, int64_t ldb)
 {
     if (!h) return -1;
-    if (!(W == 1 || W == 2 || W == 4 || W == 8)) return -4;
-    if (!slot_covers(PF, n, kl, ku) || nrhs < 1) return -5;
+    if (!(W == 1 || W == 2 || W == 4)) return -4;
+    if (!slot_covers(PF, n, kl, ku) || nrhs < 1) return -7;
     DeviceGuard g(h->device);
-    if (PF == 2 && PB == 2) return run_slot_w<2, 2>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (PF == 4 && PB == 2) return run_slot_w<4, 2>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (PF == 4 && PB == 4) return run_slot_w<4, 4>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (PF == 8 && PB == 4) return run_slot_w<8, 4>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (PF == 8 && PB == 2) return run_slot_w<8, 2>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (PF == 8 && PB == 8) return run_slot_w<8, 8>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (PF == 4 && PB == 8) return run_slot_w<4, 8>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+#define SLOT_VARIANT(pf, pb, rf, rb) \
+    if (PF == pf && PB == pb && RF == rf && RB == rb) return run_slot_w<pf, pb, rf, rb>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    SLOT_VARIANT(2, 2, 1, 1)
+    SLOT_VARIANT(4, 4, 1, 1)
+    SLOT_VARIANT(4, 8, 1, 1)
+    SLOT_VARIANT(8, 8, 1, 1)
+    SLOT_VARIANT(8, 4, 1, 1)
+    SLOT_VARIANT(4, 4, 2, 2)
+    SLOT_VARIANT(4, 8, 2, 1)
+    SLOT_VARIANT(4, 8, 2, 2)
+    SLOT_VARIANT(8, 8, 2, 2)
+    SLOT_VARIANT(4, 4, 4, 4)
+    SLOT_VARIANT(4, 4, 4, 2)
+#undef SLOT_VARIANT
     return -2;
 }
 

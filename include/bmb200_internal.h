@@ -23,11 +23,11 @@ int bmb200_internal_divcheck(bmb200_handle_t h, int64_t n, const double *dx, con
 int bmb200_internal_divcheck2(bmb200_handle_t h, int64_t n, const double *dx, const double *dd,
                               unsigned long long *dbad);
 
-/* bmb200_dgbtrs('N', ...) forced through the slot-scheduled kernels with PF / PB steps per
- * forward / backward round ((2,2), (4,2), (4,4), (8,2), (8,4)) and W right-hand sides per CTA
- * (1, 2, 4 or 8).                                                                             */
-int bmb200_internal_gbtrs_slot(bmb200_handle_t h, int PF, int PB, int W, int64_t n, int64_t kl,
-                               int64_t ku, int64_t nrhs, const double *dAB, int64_t ldab,
+/* bmb200_dgbtrs('N', ...) forced through one variant of the slot-scheduled kernels (gbtrs_slot.cu):
+ * PF / PB steps per forward / backward round, W warps per CTA (1, 2, 4), RF / RB right-hand sides
+ * per warp in the forward / backward sweep.  -2: variant not instantiated.                      */
+int bmb200_internal_gbtrs_slot(bmb200_handle_t h, int PF, int PB, int W, int RF, int RB, int64_t n,
+                               int64_t kl, int64_t ku, int64_t nrhs, const double *dAB, int64_t ldab,
                                const int64_t *d_ipiv, double *dB, int64_t ldb);
 
 /* development knobs of this handle (A/B timing and diagnostics; csrc/common.cuh `bmb_tuning` lists the keys and

@@ -312,12 +312,13 @@ def test_blocked_solve_fast_division_is_the_ieee_quotient(bm, rng):
     assert int(bad2[1].item()) > 0.2 * n  # an operand beyond 2^+-500 (3/4 of this sample) takes the IEEE route
 
 
-@pytest.mark.parametrize("PF,PB,W", [(2, 2, 1), (4, 2, 2), (4, 4, 1), (4, 4, 4), (4, 8, 8), (8, 4, 2), (8, 8, 4)])
+@pytest.mark.parametrize("PF,PB,W,RF,RB", [(2, 2, 1, 1, 1), (4, 4, 1, 1, 1), (4, 8, 2, 1, 1), (8, 8, 4, 1, 1), (8, 4, 2, 1, 1),
+                                             (4, 4, 2, 2, 2), (4, 8, 1, 2, 1), (8, 8, 2, 2, 2), (4, 4, 4, 4, 4), (4, 4, 1, 4, 2)])
 @pytest.mark.parametrize("shape", [(1000, 16, 16, 5), (777, 4, 3, 9), (64, 3, 2, 2), (3000, 24, 8, 3), (130, 5, 7, 17),
                                    (1, 0, 0, 1), (5, 4, 4, 1), (2000, 0, 3, 2), (2000, 3, 0, 2), (4097, 1, 1, 4),
                                    (63, 2, 30, 1), (65, 20, 12, 33)])
-def test_slot_scheduled_solve_bit_identical(bm, oracle_c, rng, shape, PF, PB, W):
-    """gbtrs_slot.cu, every (PF, PB, W) variant through the internal hook: solutions bit-identical to DGBTRS 'N' with
+def test_slot_scheduled_solve_bit_identical(bm, oracle_c, rng, shape, PF, PB, W, RF, RB):
+    """gbtrs_slot.cu, (PF, PB, W, RF, RB) variants through the internal hook: solutions bit-identical to DGBTRS 'N' with
     interchanges, ragged n around the 64-column schedule stages, kl = 0, ku = 0, more RHS than a CTA holds."""
     import ctypes as C
 
@@ -334,7 +335,7 @@ def test_slot_scheduled_solve_bit_identical(bm, oracle_c, rng, shape, PF, PB, W)
     dab = torch.as_tensor(np.ascontiguousarray(ab.T)).cuda()  # (n, ldab): column j of AB contiguous
     dip = torch.as_tensor(ipiv.astype(np.int64)).cuda()
     X = bm.to_colmajor(B)
-    rc = hd.lib.bmb200_internal_gbtrs_slot(hd.h, PF, PB, W, n, l, u, nrhs, C.c_void_p(dab.data_ptr()), ab.shape[0],
+    rc = hd.lib.bmb200_internal_gbtrs_slot(hd.h, PF, PB, W, RF, RB, n, l, u, nrhs, C.c_void_p(dab.data_ptr()), ab.shape[0],
                                            C.c_void_p(dip.data_ptr()), C.c_void_p(X.data_ptr()), max(1, n))
     hd.check(rc, "internal_gbtrs_slot")
     torch.cuda.synchronize()

@@ -58,11 +58,11 @@ def run(label, fn):
 
 run("dispatch (bmb200_dgbtrs)", lambda: bm.ldiv_(F, X))
 dip = F.d_ipiv()
-for PF, PB in ((4, 4), (8, 4), (8, 8), (4, 8)):
+for PF, PB, RF, RB in ((4, 8, 1, 1), (4, 4, 2, 2), (4, 8, 2, 1), (4, 8, 2, 2), (8, 8, 2, 2), (4, 4, 4, 4), (4, 4, 4, 2)):
     if l + PF > 32:
         continue
-    for W in (2, 4, 8):
-        def f(PF=PF, PB=PB, W=W):
-            hd.check(hd.lib.bmb200_internal_gbtrs_slot(hd.h, PF, PB, W, n, l, u, nrhs, C.c_void_p(F.factors.ptr), F.factors.lda,
+    for W in (1, 2, 4):
+        def f(PF=PF, PB=PB, RF=RF, RB=RB, W=W):
+            hd.check(hd.lib.bmb200_internal_gbtrs_slot(hd.h, PF, PB, W, RF, RB, n, l, u, nrhs, C.c_void_p(F.factors.ptr), F.factors.lda,
                                                        C.c_void_p(dip.data_ptr()), C.c_void_p(X.data_ptr()), n), "slot")
-        run(f"slot PF={PF} PB={PB} W={W}", f)
+        run(f"slot PF={PF} PB={PB} RF={RF} RB={RB} W={W}", f)
