@@ -645,16 +645,17 @@ static int run_slot_w(bmb200_ctx *h, int W, i64 n, i64 kl, i64 ku, i64 nrhs, con
 static bool slot_covers(int PF, i64 n, i64 kl, i64 ku) { return n >= 1 && kl + PF <= 32 && kl + ku <= 32; }
 
 // Returns 1 when the shape is not covered (the caller falls through to the older kernels).
+// Measured at C4 (n = 2^20, (16,16), 256 RHS; tools/time_gbtrs.py): PF=4/PB=8, one right-hand side per warp, one warp
+// per CTA: 92 ms; two / four right-hand sides per warp (interleaved chains in one instruction stream) cost 1.5x / 2.7x
+// per warp -- no gain while the right-hand sides do not fill the chip's 592 sub-partition slots, and beyond that the
+// hardware interleaves resident warps by itself -- so R stays 1.
 int bmb_gbtrs_slot(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB,
                    i64 ldb)
 {
     if (!slot_covers(4, n, kl, ku)) return 1;
     const i64 sms = h->sm_count;
-    // few right-hand sides: one per warp, one warp per SM sub-partition; many: two per warp (interleaved chains)
-    if (nrhs <= sms) return run_slot_w<4, 8, 1, 1>(h, 1, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    const i64 warps = cdiv64(nrhs, 2);
-    const int W = (warps <= sms) ? 1 : (warps <= 2 * sms) ? 2 : 4;
-    return run_slot_w<4, 4, 2, 2>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    const int W = (nrhs <= 4 * sms) ? 1 : (nrhs <= 8 * sms) ? 2 : 4;
+    return run_slot_w<4, 8, 1, 1>(h, W, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
 }
 
 // ---- development hook (include/bmb200_internal.h): explicit variant for A/B timing; not part of the public ABI ----
@@ -672,13 +673,7 @@ extern "C" int bmb200_internal_gbtrs_slot(bmb200_handle_t h, int PF, int PB, int
     SLOT_VARIANT(4, 4, 1, 1)
     SLOT_VARIANT(4, 8, 1, 1)
     SLOT_VARIANT(8, 8, 1, 1)
-    SLOT_VARIANT(8, 4, 1, 1)
     SLOT_VARIANT(4, 4, 2, 2)
-    SLOT_VARIANT(4, 8, 2, 1)
-    SLOT_VARIANT(4, 8, 2, 2)
-    SLOT_VARIANT(8, 8, 2, 2)
-    SLOT_VARIANT(4, 4, 4, 4)
-    SLOT_VARIANT(4, 4, 4, 2)
 #undef SLOT_VARIANT
     return -2;
 }

@@ -12,7 +12,7 @@ def main():
     ins = []
     i = 0
     while i < len(lines):
-        m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);\s+/\* 0x([0-9a-f]{16}) \*/", lines[i])
+        m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);\s+/\* 0x([0-9a-f]{16}) \*/", lines[i])
         if m and i + 1 < len(lines):
             m2 = re.match(r"\s+/\* 0x([0-9a-f]{16}) \*/", lines[i + 1])
             if m2:

@@ -58,7 +58,7 @@ def run(label, fn):
 
 run("dispatch (bmb200_dgbtrs)", lambda: bm.ldiv_(F, X))
 dip = F.d_ipiv()
-for PF, PB, RF, RB in ((4, 8, 1, 1), (4, 4, 2, 2), (4, 8, 2, 1), (4, 8, 2, 2), (8, 8, 2, 2), (4, 4, 4, 4), (4, 4, 4, 2)):
+for PF, PB, RF, RB in ((4, 8, 1, 1), (4, 4, 1, 1), (8, 8, 1, 1), (4, 4, 2, 2)):
     if l + PF > 32:
         continue
     for W in (1, 2, 4):
