@@ -28,6 +28,7 @@ PROTOTYPES = {
     "bmb200_dgbmv": (C.c_int, [vp, ch, i64, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
     "bmb200_dgbmm_bb": (C.c_int, [vp] + [i64] * 9 + [dbl, vp, i64, vp, i64, dbl, vp, i64]),
     "bmb200_dgbmm_bd": (C.c_int, [vp, ch, i64, i64, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
+    "bmb200_dgbmm_db": (C.c_int, [vp, ch, i64, i64, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
     "bmb200_dfill_lmul": (C.c_int, [vp, dbl, vp, i64, i64, i64, i64]),
     "bmb200_dband_widen": (C.c_int, [vp, i64, i64, i64, vp, i64, vp, i64]),
     "bmb200_dgbtrf": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(C.c_int)]),
@@ -37,6 +38,10 @@ PROTOTYPES = {
     "bmb200_dsbmv": (C.c_int, [vp, ch, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
     "bmb200_dband_axpy": (C.c_int, [vp, i64, i64, dbl, i64, i64, vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64)]),
     "bmb200_dband_copy": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64)]),
+    "bmb200_dband_lmul_block": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i64, dbl]),
+    "bmb200_dband_transpose": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, i64]),
+    "bmb200_dband_nonzero_rows": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, C.POINTER(C.c_int)]),
+    "bmb200_dband_axpby": (C.c_int, [vp, i64, i64, dbl, i64, i64, vp, i64, dbl, i64, i64, vp, i64, i64, i64, vp, i64]),
     "bmb200_dgbmv_host": (C.c_int, [vp, ch, i64, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
     "bmb200_dgbsv_host": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, vp, i64, C.POINTER(C.c_int)]),
     "bmb200_dgbmm_bb_host": (C.c_int, [vp] + [i64] * 9 + [dbl, vp, i64, vp, i64, dbl, vp, i64]),

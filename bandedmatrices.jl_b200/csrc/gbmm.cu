@@ -674,3 +674,64 @@ extern "C" int bmb200_dgbmm_bd(bmb200_handle_t h, char trans, int64_t m, int64_t
     BMB_LAUNCH_CHECK(h);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// dense x banded: C <- alpha * A * op(P) + beta * C, A dense M x K, C dense M x N (both column-major).
+// Replaces the per-ROW loop of src/generic/matmul.jl:258-271 (one strided gbmv per row of C: M BLAS calls) by one launch.
+//   trans == 'N': op(P) = P, K x N with (kl,ku): row i of C is gbmv('T', P, A[i,:]) -- a dot product per entry (the order of
+//                 OpenBLAS' dgbmv_t dot is unspecified; same formula as gbmv_t_* here: temp = sum fma, C = fma(alpha, temp, beta*C)).
+//   trans == 'T': op(P) = P^T, P is N x K with (kl,ku): row i of C is gbmv('N', P, A[i,:]) -- every C[i,j] accumulates over k
+//                 ascending with t = alpha*A[i,k] rounded first, one FMA per term: bit-identical to the reference's dgbmv_n rows.
+// thread = one entry of C, i fastest: A and C accesses are coalesced down the columns, the band entry is a warp broadcast.
+// ------------------------------------------------------------------------------------------------
+template <bool TR>
+__global__ void __launch_bounds__(256)
+gbmm_db_kernel(i64 M, i64 K, i64 N, i64 kl, i64 ku, double alpha, const double *__restrict__ a, i64 lda,
+               const double *__restrict__ p, i64 ldp, double beta, double *__restrict__ c, i64 ldc)
+{
+    const i64 total = M * N;
+    for (i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        const i64 j = t / M, i = t - j * M;
+        double *cp = c + i + j * ldc;
+        const double c0 = (beta == 0.0) ? 0.0 : __dmul_rn(beta, *cp);
+        if (!TR) {
+            i64 k0 = j - ku; if (k0 < 0) k0 = 0;
+            i64 k1 = j + kl; if (k1 > K - 1) k1 = K - 1;
+            const double *col = p + j * ldp + (ku - j);  // P[k,j] = col[k]
+            double temp = 0.0;
+            for (i64 k = k0; k <= k1; ++k) temp = fma(col[k], a[i + k * lda], temp);
+            *cp = fma(alpha, temp, c0);
+        } else {
+            i64 k0 = j - kl; if (k0 < 0) k0 = 0;
+            i64 k1 = j + ku; if (k1 > K - 1) k1 = K - 1;
+            double acc = c0;
+            for (i64 k = k0; k <= k1; ++k)  // P[j,k] = p[(ku + j - k) + k*ldp]
+                acc = fma(__dmul_rn(alpha, a[i + k * lda]), p[(ku + j - k) + k * ldp], acc);
+            *cp = acc;
+        }
+    }
+}
+
+extern "C" int bmb200_dgbmm_db(bmb200_handle_t h, char trans, int64_t M, int64_t K, int64_t N, int64_t kl, int64_t ku,
+                               double alpha, const double *dA, int64_t lda, const double *dP, int64_t ldp, double beta,
+                               double *dC, int64_t ldc)
+{
+    if (!h) return -1;
+    const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
+    if (!tr && !(trans == 'N' || trans == 'n')) return -2;
+    if (M < 0) return -3;
+    if (K < 0) return -4;
+    if (N < 0) return -5;
+    if (kl < 0) return -6;
+    if (ku < 0) return -7;
+    if (lda < imax64(1, M)) return -10;
+    if (ldp < kl + ku + 1) return -12;
+    if (ldc < imax64(1, M)) return -15;
+    if (M == 0 || N == 0) return 0;
+    DeviceGuard g(h->device);
+    const i64 blocks = imin64(cdiv64(M * N, 256), (i64)h->sm_count * 16);
+    if (tr) gbmm_db_kernel<true><<<(unsigned)blocks, 256, 0, h->stream>>>(M, K, N, kl, ku, alpha, dA, lda, dP, ldp, beta, dC, ldc);
+    else gbmm_db_kernel<false><<<(unsigned)blocks, 256, 0, h->stream>>>(M, K, N, kl, ku, alpha, dA, lda, dP, ldp, beta, dC, ldc);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}

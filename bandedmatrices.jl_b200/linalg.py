@@ -15,7 +15,8 @@ here                                   reference
 ``ldiv_(F, B)`` / ``solve(A, b)``      ``ldiv!`` / ``\\`` src/banded/linalg.jl:5-9, 24-30, 41-47
 =====================================  ===========================================================
 
-Every arithmetic step is a kernel of ``libbmb200.so``; nothing here computes on the CPU.
+Every arithmetic step -- including the band bookkeeping of the gbmm! driver (zero-band counts, block scaling, the transposed
+copy) -- is a kernel of ``libbmb200.so``; nothing here computes on the CPU or through eager tensor ops.
 """
 from __future__ import annotations
 
@@ -80,16 +81,9 @@ def _fill_banded_rows(Cm: BandedMatrix, r0: int, r1: int, c0: int, c1: int, beta
     """lmul!(beta, view(C, r0+1:r1, c0+1:c1)) on a BandedMatrix: scale/zero the in-band entries of that block."""
     if r1 <= r0 or c1 <= c0 or Cm.data.numel() == 0 or (beta == 0 and zero):
         return
-    rows = Cm.data.shape[1]
-    j = torch.arange(c0, c1, device=Cm.data.device).unsqueeze(1)
-    r = torch.arange(rows, device=Cm.data.device).unsqueeze(0)
-    k = j + r - Cm.u
-    mask = (k >= r0) & (k < r1)
-    blk = Cm.data[c0:c1]
-    if beta == 0:
-        blk[mask] = 0.0
-    else:
-        blk[mask] = blk[mask] * beta
+    hd = _h(Cm.data)
+    hd.check(hd.lib.bmb200_dband_lmul_block(hd.h, Cm.m, Cm.n, Cm.l, Cm.u, vp(Cm.ptr), Cm.lda, r0, r1, c0, c1, float(beta)),
+             "dband_lmul_block")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -147,26 +141,32 @@ def _banded_muladd_row(alpha, At: BandedMatrix, x, beta, y, yzero=False):
 # ---------------------------------------------------------------------------------------------
 # banded * banded : gbmm!  (src/banded/gbmm.jl:207-293)
 # ---------------------------------------------------------------------------------------------
+def _nonzero_band_rows(A: BandedMatrix) -> list:
+    rows = A.l + A.u + 1
+    if rows <= 0:
+        return []
+    hd = _h(A.data)
+    flags = (C.c_int * rows)()
+    hd.check(hd.lib.bmb200_dband_nonzero_rows(hd.h, A.m, A.n, A.l, A.u, vp(A.ptr), A.lda, flags), "dband_nonzero_rows")
+    return list(flags)
+
+
 def _num_zeroband_u(A: BandedMatrix) -> int:
     """gbmm.jl:191-197: number of leading all-zero upper bands (data rows from the top)."""
-    for b in range(A.l + A.u + 1):
-        off = A.u - b
-        js = slice(max(0, off), max(0, min(A.n, A.m + off)))
-        if bool((A.data[js, b] != 0).any()):
+    f = _nonzero_band_rows(A)
+    for b, nz in enumerate(f):
+        if nz:
             return b
-    return A.l + A.u + 1
+    return len(f)
 
 
 def _num_zeroband_l(A: BandedMatrix) -> int:
     """gbmm.jl:199-205: number of trailing all-zero lower bands (data rows from the bottom)."""
-    rows = A.l + A.u + 1
-    for b in range(rows):
-        r = rows - 1 - b
-        off = A.u - r
-        js = slice(max(0, off), max(0, min(A.n, A.m + off)))
-        if bool((A.data[js, r] != 0).any()):
+    f = _nonzero_band_rows(A)
+    for b, nz in enumerate(reversed(f)):
+        if nz:
             return b
-    return rows
+    return len(f)
 
 
 def gbmm_(alpha, A: BandedMatrix, B: BandedMatrix, beta, Cm: BandedMatrix, Czero: bool = False):
@@ -291,15 +291,27 @@ def _banded_times_dense(alpha, A, B, beta, Cd):
 
 
 def _dense_times_banded(alpha, Ad, B, beta, Cd):
-    """matmul.jl:258-271: for each row, mul!(rowC, transpose(B), rowA, α, β) (strided x and y)."""
+    """matmul.jl:258-271: for each row, mul!(rowC, transpose(B), rowA, α, β) (strided x and y).  One bmb200_dgbmm_db launch
+    covers all rows when the band widths are non-negative; the negative-bandwidth re-viewing of _banded_muladd!
+    (matmul.jl:41-59, 66-86) keeps the reference's per-row form."""
     if alpha == 0:
         _fill_cm(Cd, beta)
         return Cd
+    tr = isinstance(B, Transposed)
+    P = B.parent if tr else B
+    if Cd.shape[0] == 0 or Cd.shape[1] == 0:
+        return Cd
+    if P.l >= 0 and P.u >= 0 and Ad.shape[1] > 0:
+        hd = _h(Cd)
+        hd.check(hd.lib.bmb200_dgbmm_db(hd.h, (b"T" if tr else b"N"), Cd.shape[0], Ad.shape[1], Cd.shape[1], P.l, P.u,
+                                        float(alpha), vp(Ad.data_ptr()), _ld(Ad), vp(P.ptr), P.lda, float(beta),
+                                        vp(Cd.data_ptr()), _ld(Cd)), "dgbmm_db")
+        return Cd
     for i in range(Cd.shape[0]):
-        if isinstance(B, Transposed):
-            _banded_muladd_vec(alpha, B.parent, Ad[i], beta, Cd[i])
+        if tr:
+            _banded_muladd_vec(alpha, P, Ad[i], beta, Cd[i])
         else:
-            _banded_muladd_row(alpha, B, Ad[i], beta, Cd[i])
+            _banded_muladd_row(alpha, P, Ad[i], beta, Cd[i])
     return Cd
 
 
@@ -340,16 +352,10 @@ def mul_(Cout, A, B, alpha=1.0, beta=0.0):
 def materialize_transpose(At: Transposed) -> BandedMatrix:
     """convert(DefaultBandedMatrix, A') (matmul.jl:182-184): band row r of A' is band row (l+u-r) of A, shifted."""
     P = At.parent
-    m, n, l, u = P.m, P.n, P.l, P.u
-    rows = max(0, l + u + 1)
-    out = BandedMatrix.zeros((n, m), (u, l), device=P.data.device)
-    # A'[k', j'] = A[j', k'];  out.data[j', l + k' - j'] = P.data[k', u + j' - k']
-    for r in range(rows):  # r = band row of out: k' - j' = r - l
-        d = r - l
-        src_r = u - d  # band row in P: u + j' - k' = u - d
-        j0, j1 = max(0, -d), min(m, n - d)  # j' range with k' = j'+d in [0, n)
-        if j1 > j0:
-            out.data[j0:j1, r] = P.data[j0 + d : j1 + d, src_r]
+    out = BandedMatrix.undef((P.n, P.m), (P.u, P.l), device=P.data.device)
+    if P.l + P.u + 1 > 0 and P.m > 0 and P.n > 0:
+        hd = _h(P.data)
+        hd.check(hd.lib.bmb200_dband_transpose(hd.h, P.m, P.n, P.l, P.u, vp(P.ptr), P.lda, vp(out.ptr), out.lda), "dband_transpose")
     return out
 
 
@@ -611,6 +617,56 @@ def copyto_(dest: BandedMatrix, src: BandedMatrix) -> BandedMatrix:
     if out.value:
         raise BandError(dest, (src.l if src.l > dest.l else -src.u))
     return dest
+
+
+def similar(A: BandedMatrix, bandwidths=None) -> BandedMatrix:
+    """``similar(A)`` / ``similar(A, T, m, n, l, u)``: an uninitialised device BandedMatrix of the same size."""
+    bw = (A.l, A.u) if bandwidths is None else tuple(bandwidths)
+    return BandedMatrix.undef(A.shape, bw, device=A.data.device)
+
+
+def axpby_(alpha, X: BandedMatrix, beta, Y: BandedMatrix, Z: BandedMatrix | None = None) -> BandedMatrix:
+    """``Z .= alpha .* X .+ beta .* Y`` (src/generic/broadcast.jl:359-384, 927-964).  Without ``Z`` the result is allocated
+    with the reference's broadcast bandwidths ``max.(bandwidths(X), bandwidths(Y))``; a given ``Z`` with fewer bands raises
+    ``BandError`` when a dropped band holds a non-zero (checked on the device)."""
+    if X.shape != Y.shape:
+        raise DimensionMismatch(f"arrays could not be broadcast to a common size: {X.shape} and {Y.shape}")
+    bw = (max(X.l, Y.l), max(X.u, Y.u))
+    if Z is None:
+        Z = BandedMatrix.undef(X.shape, bw, device=X.data.device)
+    elif Z.shape != X.shape:
+        raise DimensionMismatch(f"destination has size {Z.shape}, operands {X.shape}")
+    elif Z.l < bw[0] or Z.u < bw[1]:
+        for M_, c_ in ((X, alpha), (Y, beta)):  # non-zeros in bands the destination does not store -> BandError
+            if c_ != 0 and (M_.l > Z.l or M_.u > Z.u):
+                out = C.c_int64(0)
+                hd = _h(Z.data)
+                tmp = BandedMatrix.undef(Z.shape, (Z.l, Z.u), device=Z.data.device)
+                hd.check(hd.lib.bmb200_dband_copy(hd.h, M_.m, M_.n, M_.l, M_.u, vp(M_.ptr), _ld_band(M_), tmp.l, tmp.u, vp(tmp.ptr),
+                                                  _ld_band(tmp), C.byref(out)), "dband_copy")
+                if out.value:
+                    raise BandError(Z, (M_.l if M_.l > Z.l else -M_.u))
+    if Z.m == 0 or Z.n == 0 or Z.l + Z.u + 1 <= 0:
+        return Z
+    hd = _h(Z.data)
+    hd.check(hd.lib.bmb200_dband_axpby(hd.h, X.m, X.n, float(alpha), X.l, X.u, vp(X.ptr), _ld_band(X), float(beta), Y.l, Y.u,
+                                       vp(Y.ptr), _ld_band(Y), Z.l, Z.u, vp(Z.ptr), _ld_band(Z)), "dband_axpby")
+    return Z
+
+
+def badd(A: BandedMatrix, B: BandedMatrix) -> BandedMatrix:
+    """``A .+ B`` / ``A + B``."""
+    return axpby_(1.0, A, 1.0, B)
+
+
+def bsub(A: BandedMatrix, B: BandedMatrix) -> BandedMatrix:
+    """``A .- B`` / ``A - B``."""
+    return axpby_(1.0, A, -1.0, B)
+
+
+def bscale(alpha, A: BandedMatrix) -> BandedMatrix:
+    """``alpha .* A`` / ``alpha * A`` (same bandwidths)."""
+    return axpby_(alpha, A, 0.0, A, similar(A))
 
 
 def factorize(A: BandedMatrix):

@@ -80,6 +80,14 @@ int bmb200_dgbmm_bd(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t
                     int64_t nrhs, double alpha, const double *dA, int64_t lda, const double *dB,
                     int64_t ldb, double beta, double *dC, int64_t ldc);
 
+/* ---- C <- alpha*A*op(P) + beta*C, A / C dense column-major (M x K, M x N), P banded -------------
+ * Replaces the per-row mul! loop of src/generic/matmul.jl:258-271 (dense x banded: one strided dgbmv_ per ROW of C).
+ * trans 'N': op(P) = P, K x N with (kl,ku) (rows of C are dgbmv_('T') dot products: equal to 1e-13);
+ * trans 'T': op(P) = P^T, P N x K with (kl,ku) (rows of C are dgbmv_('N'): bit-identical, k ascending).          */
+int bmb200_dgbmm_db(bmb200_handle_t h, char trans, int64_t M, int64_t K, int64_t N, int64_t kl, int64_t ku,
+                    double alpha, const double *dA, int64_t lda, const double *dP, int64_t ldp, double beta,
+                    double *dC, int64_t ldc);
+
 /* ---- C <- beta*C on a rows x cols column-major block; beta == 0 zero-fills ----------------
  * Replaces _fill_lmul!/_fill_rmul! : src/generic/utils.jl:29-31 (used by gbmm.jl:287-288,339
  * and matmul.jl:31-33,45,52).  inc is the element stride inside a column (1 for matrices).  */
@@ -139,6 +147,27 @@ int bmb200_dband_axpy(bmb200_handle_t h, int64_t m, int64_t n, double a, int64_t
                       int64_t ldx, int64_t yl, int64_t yu, double *dY, int64_t ldy, int64_t *nonzero_outside);
 int bmb200_dband_copy(bmb200_handle_t h, int64_t m, int64_t n, int64_t sl, int64_t su, const double *dS, int64_t lds,
                       int64_t dl, int64_t du, double *dD, int64_t ldd, int64_t *nonzero_outside);
+
+/* ---- band utilities of the gbmm! driver and the broadcasting layer (all on the device) --------------------------------
+ * bmb200_dband_lmul_block : lmul!(beta, view(C, r0+1:r1, c0+1:c1)) on the stored band, beta == 0 zero-fills -- the blocks a
+ *                           negative-bandwidth operand leaves untouched in gbmm! (src/banded/gbmm.jl:234-249).
+ * bmb200_dband_transpose  : D = A' as a plain BandedMatrix (convert at src/generic/matmul.jl:182-184): A is m x n with (l,u),
+ *                           D is n x m with (u,l); corner slots of D are zeroed.
+ * bmb200_dband_nonzero_rows: flags_host[r] = 1 when band row r of the data array holds a non-zero in-matrix entry
+ *                           (gbmm.jl:191-205 counts the leading / trailing all-zero bands from these); synchronises.
+ * bmb200_dband_axpby      : Z = alpha*X + beta*Y entry by entry over Z's band, X / Y read as zero outside their bands --
+ *                           the arithmetic of the reference's broadcast kernels for A .+ B, A .- B, a .* A, a .* A .+ b .* B
+ *                           (src/generic/broadcast.jl:359-384, 927-964; products and sum rounded separately).  Z may alias X or Y
+ *                           when the bandwidths are equal.                                                                        */
+int bmb200_dband_lmul_block(bmb200_handle_t h, int64_t m, int64_t n, int64_t l, int64_t u, double *dC, int64_t ldc,
+                            int64_t r0, int64_t r1, int64_t c0, int64_t c1, double beta);
+int bmb200_dband_transpose(bmb200_handle_t h, int64_t m, int64_t n, int64_t l, int64_t u, const double *dS, int64_t lds,
+                           double *dD, int64_t ldd);
+int bmb200_dband_nonzero_rows(bmb200_handle_t h, int64_t m, int64_t n, int64_t l, int64_t u, const double *dX, int64_t ldx,
+                              int *flags_host);
+int bmb200_dband_axpby(bmb200_handle_t h, int64_t m, int64_t n, double alpha, int64_t xl, int64_t xu, const double *dX,
+                       int64_t ldx, double beta, int64_t yl, int64_t yu, const double *dY, int64_t ldy, int64_t zl,
+                       int64_t zu, double *dZ, int64_t ldz);
 
 /* ---- host-buffer forms: what a Fortran-ABI caller with HOST arrays gets (bench.py "e2e") ----
  * Same semantics as the calls above; inputs are copied host->device in pipelined chunks, the

@@ -84,7 +84,17 @@ class _CBackend:
             f.argtypes = [C.c_char, C.c_char, C.c_char, i64, i64, C.c_void_p, i64, C.c_void_p]
         L.oracle_dsbmv.restype = C.c_int
         L.oracle_dsbmv.argtypes = [C.c_char, i64, i64, C.c_double, C.c_void_p, i64, C.c_void_p, C.c_double, C.c_void_p]
+        L.oracle_dpbtf2.restype = C.c_int
+        L.oracle_dpbtf2.argtypes = [C.c_char, i64, i64, C.c_void_p, i64]
+        L.oracle_dpbtrs.restype = C.c_int
+        L.oracle_dpbtrs.argtypes = [C.c_char, i64, i64, i64, C.c_void_p, i64, C.c_void_p, i64]
         self.L = L
+
+    def pbtrf(self, uplo, n, kd, ab, ldab):
+        return self.L.oracle_dpbtf2(uplo.encode(), n, kd, _ptr(ab), ldab)
+
+    def pbtrs(self, uplo, n, kd, nrhs, ab, ldab, b, ldb):
+        return self.L.oracle_dpbtrs(uplo.encode(), n, kd, nrhs, _ptr(ab), ldab, _ptr(b), ldb)
 
     def sbmv(self, uplo, n, k, alpha, a, lda, x, beta, y):
         return self.L.oracle_dsbmv(uplo.encode(), n, k, alpha, _ptr(a), lda, _ptr(x), beta, _ptr(y))
@@ -152,6 +162,19 @@ class _OpenBLASBackend:
 
     def tbmv(self, uplo, trans, diag, n, k, a, lda, x):  # dtbmv_ as src/blas.jl:94-99 calls it
         return self._tb(self.L.scipy_dtbmv_64_, uplo, trans, diag, n, k, a, lda, x)
+
+    def pbtrf(self, uplo, n, kd, ab, ldab):  # dpbtrf_ as pbtrf! calls it (src/lapack.jl:280-290)
+        r = C.byref
+        info = i64(0)
+        self.L.scipy_dpbtrf_64_(C.c_char_p(uplo.encode()), r(i64(n)), r(i64(kd)), _ptr(ab), r(i64(ldab)), r(info), C.c_long(1))
+        return int(info.value)
+
+    def pbtrs(self, uplo, n, kd, nrhs, ab, ldab, b, ldb):  # dpbtrs_ as pbtrs! calls it (src/lapack.jl:312-326)
+        r = C.byref
+        info = i64(0)
+        self.L.scipy_dpbtrs_64_(C.c_char_p(uplo.encode()), r(i64(n)), r(i64(kd)), r(i64(nrhs)), _ptr(ab), r(i64(ldab)), _ptr(b),
+                                r(i64(ldb)), r(info), C.c_long(1))
+        return int(info.value)
 
     def gbtf2(self, m, n, kl, ku, ab, ldab, ipiv):
         r = C.byref

@@ -411,3 +411,56 @@ void oracle_banded_mul(i64 Am, i64 An, i64 Bn, i64 Al, i64 Au, i64 Bl, i64 Bu, i
             c[(Cu_ + k - j) + j * ldc] = tmp;
         }
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Banded Cholesky: pbtrf! / pbtrs! (src/lapack.jl:268-332) behind cholesky(Symmetric(::BandedMatrix)) and its ldiv!
+ * (src/symbanded/BandedCholesky.jl:2-13, 72-80).  Reference-LAPACK DPBTF2 (the unblocked algorithm DPBTRF runs for kd < 32; its
+ * blocked form for wider bands differs by DGEMM / DSYRK rounding only):
+ *   for j: ajj = A[j,j]; ajj <= 0 -> info = j+1, stop; d = sqrt(ajj); row j of U (resp. column j of L) *= 1/d (DSCAL by the
+ *   reciprocal); trailing kn x kn triangle -= x x^T (DSYR, OpenBLAS: one AXPY per column with t = -x[k] and a FMA per entry).
+ * uplo 'U': A[i,k] (i <= k) at ab[(kd + i - k) + k*ldab];  'L': A[i,k] (i >= k) at ab[(i - k) + k*ldab].
+ * --------------------------------------------------------------------------------------------------------------------- */
+int oracle_dpbtf2(char uplo, i64 n, i64 kd, double *ab, i64 ldab)
+{
+    const int up = (uplo == 'U' || uplo == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -1;
+    if (n < 0) return -2;
+    if (kd < 0) return -3;
+    if (ldab < kd + 1) return -5;
+#define PB(i, k) ab[up ? ((kd + (i) - (k)) + (k) * ldab) : (((k) - (i)) + (i) * ldab)] /* symmetric entry (i <= k) */
+    for (i64 j = 0; j < n; ++j) {
+        double ajj = PB(j, j);
+        if (ajj <= 0.0) return (int)(j + 1);
+        ajj = sqrt(ajj);
+        PB(j, j) = ajj;
+        const i64 kn = imin(kd, n - 1 - j);
+        const double rinv = 1.0 / ajj;
+        for (i64 c = 1; c <= kn; ++c) PB(j, j + c) = PB(j, j + c) * rinv;
+        for (i64 c = 1; c <= kn; ++c) {          /* DSYR: column (resp. row) j+c of the trailing triangle */
+            const double xc = PB(j, j + c);
+            if (xc == 0.0) continue;             /* OpenBLAS dsyr skips zero entries of x */
+            const double t = -xc;
+            for (i64 r = 1; r <= c; ++r) PB(j + r, j + c) = fma(t, PB(j, j + r), PB(j + r, j + c));
+        }
+    }
+#undef PB
+    return 0;
+}
+
+/* DPBTRS: for every right-hand side, DTBSV with U^T then U ('U') or L then L^T ('L') (src/lapack.jl:300-332). */
+int oracle_dpbtrs(char uplo, i64 n, i64 kd, i64 nrhs, const double *ab, i64 ldab, double *b, i64 ldb)
+{
+    const int up = (uplo == 'U' || uplo == 'u');
+    for (i64 q = 0; q < nrhs; ++q) {
+        double *x = b + q * ldb;
+        if (up) {
+            oracle_dtbsv('U', 'T', 'N', n, kd, ab, ldab, x);
+            oracle_dtbsv('U', 'N', 'N', n, kd, ab, ldab, x);
+        } else {
+            oracle_dtbsv('L', 'N', 'N', n, kd, ab, ldab, x);
+            oracle_dtbsv('L', 'T', 'N', n, kd, ab, ldab, x);
+        }
+    }
+    return 0;
+}

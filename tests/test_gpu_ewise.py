@@ -68,3 +68,55 @@ def test_band_error_when_nonzeros_fall_outside(bm, rng):
     assert np.array_equal(_dense(dY.banddata_host(), m, 2, 2), 2.0 * X.dense() + Y0.dense())
     with pytest.raises(bm.DimensionMismatch):
         bm.axpy_(1.0, dX, bm.BandedMatrix.zeros((m, n + 1), (3, 2)))
+
+
+def _rand_banded_dense(rng, m, n, l, u):
+    D = rng.standard_normal((m, n))
+    k, j = np.meshgrid(np.arange(m), np.arange(n), indexing="ij")
+    D[(k - j > l) | (j - k > u)] = 0.0
+    return D
+
+
+def test_materialize_transpose_and_zeroband_counts(bm, rng):
+    """convert(BandedMatrix, A') and gbmm.jl:191-205's zero-band counts, computed by device kernels."""
+    from bandedmatrices_b200.linalg import _num_zeroband_l, _num_zeroband_u, materialize_transpose
+
+    for (m, n, l, u) in [(8, 11, 2, 3), (11, 8, 0, 4), (6, 6, 1, 0), (300, 200, 17, 40), (1, 1, 0, 0)]:
+        D = _rand_banded_dense(rng, m, n, l, u)
+        A = bm.BandedMatrix.from_dense(D, (l, u))
+        T = materialize_transpose(A.T)
+        assert (T.l, T.u) == (u, l)
+        assert np.array_equal(T.to_dense(), D.T)
+    D = _rand_banded_dense(rng, 9, 9, 2, 3)
+    D[np.arange(6), np.arange(6) + 3] = 0  # top band all zero
+    D[np.arange(7), np.arange(7) + 2] = 0
+    A = bm.BandedMatrix.from_dense(D, (2, 3))
+    assert _num_zeroband_u(A) == 2 and _num_zeroband_l(A) == 0
+    Z = bm.BandedMatrix.from_dense(np.zeros((5, 5)), (1, 1))
+    assert _num_zeroband_u(Z) == 3 and _num_zeroband_l(Z) == 3
+
+
+@pytest.mark.parametrize("bands", [((2, 3), (2, 3)), ((1, 4), (3, 0)), ((0, 0), (5, 2)), ((7, 1), (-1, 3)), ((40, 33), (2, 2))])
+def test_broadcast_axpby_add_sub_scale(bm, rng, bands):
+    """A .+ B, A .- B, a .* A, a .* A .+ b .* B (src/generic/broadcast.jl:359-384, 927-964): result bandwidths are the
+    element-wise maxima, every entry is round(round(a*x) + round(b*y)) -- numpy's arithmetic on the dense forms."""
+    (xl, xu), (yl, yu) = bands
+    m, n = 120, 97
+    X = _rand_banded_dense(rng, m, n, xl, xu)
+    Y = _rand_banded_dense(rng, m, n, yl, yu)
+    A, B = bm.BandedMatrix.from_dense(X, (xl, xu)), bm.BandedMatrix.from_dense(Y, (yl, yu))
+    S = bm.badd(A, B)
+    assert (S.l, S.u) == (max(xl, yl), max(xu, yu))
+    assert np.array_equal(S.to_dense(), X + Y)
+    assert np.array_equal(bm.bsub(A, B).to_dense(), X - Y)
+    assert np.array_equal(bm.bscale(-2.5, A).to_dense(), -2.5 * X)
+    assert np.array_equal(bm.axpby_(3.0, A, 0.125, B).to_dense(), 3.0 * X + 0.125 * Y)
+    # a destination with more bands gets zeros there; with fewer bands a dropped non-zero is a BandError
+    Zw = bm.BandedMatrix.from_dense(rng.standard_normal((m, n)), (max(xl, yl) + 2, max(xu, yu) + 1))
+    bm.axpby_(1.0, A, 1.0, B, Zw)
+    assert np.array_equal(Zw.to_dense(), X + Y)
+    if max(xl, yl) >= 1:
+        Zn = bm.BandedMatrix.zeros((m, n), (max(xl, yl) - 1, max(xu, yu)))
+        with pytest.raises(bm.BandError):
+            bm.axpby_(1.0, A, 1.0, B, Zn)
+    assert bm.similar(A).shape == A.shape and (bm.similar(A, (1, 1)).l, bm.similar(A, (1, 1)).u) == (1, 1)

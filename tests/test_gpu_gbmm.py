@@ -10,7 +10,7 @@ import torch
 import oracle
 from oracle import Band, band_from_dense, brand, gbmm_kernel
 
-from _util import golden_cases
+from _util import golden_cases, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -156,3 +156,37 @@ def test_banded_times_dense(bm, oracle_c, rng, shape):
     Y = np.asfortranarray(rng.standard_normal((m, nrhs)))
     got = bm.matmul(up(bm, A).T, bm.to_colmajor(Y)).cpu().numpy()
     assert np.allclose(got, A.dense().T @ Y, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(37, 300, 4, 3), (5, 64, 0, 2), (128, 1000, 33, 17), (1, 9, 1, 1), (200, 50, 60, 70)])
+def test_dense_times_banded(bm, oracle_c, rng, shape):
+    """materialize!(MatMulMatAdd{Strided,BandedColumns,Strided}) (src/generic/matmul.jl:258-271): the reference loops one strided
+    gbmv('T') per ROW of C; bmb200_dgbmm_db does all rows in one launch.  Dense * banded is a dot product per entry (1e-13);
+    dense * transpose(banded) is the row-wise dgbmv_('N') and must be bit-identical to it."""
+    M, n, l, u = shape
+    B = brand(rng, n, n, l, u)
+    Ad = np.asfortranarray(rng.standard_normal((M, n)))
+    C0 = np.asfortranarray(rng.standard_normal((M, n)))
+    Bd = up(bm, B)
+    for alpha, beta in [(1.0, 0.0), (-0.75, 1.5)]:
+        # dense * banded
+        ref = np.empty((M, n))
+        for i in range(M):
+            y = C0[i].copy()
+            oracle.gbmv(oracle_c, "T", n, l, u, alpha, B.data, Ad[i].copy(), beta, y)
+            ref[i] = y
+        Cd = bm.to_colmajor(C0)
+        bm.mul_(Cd, bm.to_colmajor(Ad), Bd, alpha, beta)
+        assert relerr(Cd.cpu().numpy(), ref) <= 1e-13
+        # dense * transpose(banded): rows are dgbmv_('N')
+        refT = np.empty((M, n))
+        for i in range(M):
+            y = C0[i].copy()
+            oracle.gbmv(oracle_c, "N", n, l, u, alpha, B.data, Ad[i].copy(), beta, y)
+            refT[i] = y
+        CdT = bm.to_colmajor(C0)
+        bm.mul_(CdT, bm.to_colmajor(Ad), Bd.T, alpha, beta)
+        assert np.array_equal(CdT.cpu().numpy(), refT)
+    Cn = bm.to_colmajor(np.full((M, n), np.nan))
+    bm.mul_(Cn, bm.to_colmajor(Ad), Bd, 1.0, 0.0)  # beta == 0 overwrites NaN
+    assert np.isfinite(Cn.cpu().numpy()).all()

@@ -43,23 +43,17 @@ def test_views_shift_bandwidths(rng):
         assert np.array_equal(W.to_dense(), D[s:, :])
 
 
-def test_materialize_transpose(rng):
-    for (m, n, l, u) in [(8, 11, 2, 3), (11, 8, 0, 4), (6, 6, 1, 0)]:
-        D = _rand_banded(rng, m, n, l, u)
-        A = bm.BandedMatrix.from_dense(D, (l, u), device="cpu")
-        T = materialize_transpose(A.T)
-        assert (T.l, T.u) == (u, l)
-        assert np.array_equal(T.to_dense(), D.T)
-
-
-def test_num_zerobands(rng):
-    D = _rand_banded(rng, 9, 9, 2, 3)
-    D[np.arange(6), np.arange(6) + 3] = 0  # top band all zero
-    D[np.arange(7), np.arange(7) + 2] = 0
+def test_band_bookkeeping_refuses_cpu_tensors(rng):
+    """The transposed copy and the zero-band counts of the gbmm! driver are device kernels now (no eager tensor ops on the
+    product path): CPU operands are refused, not silently computed.  Their arithmetic is checked in tests/test_gpu_ewise.py."""
+    D = _rand_banded(rng, 8, 11, 2, 3)
     A = bm.BandedMatrix.from_dense(D, (2, 3), device="cpu")
-    assert _num_zeroband_u(A) == 2 and _num_zeroband_l(A) == 0
-    Z = bm.BandedMatrix.from_dense(np.zeros((5, 5)), (1, 1), device="cpu")
-    assert _num_zeroband_u(Z) == 3 and _num_zeroband_l(Z) == 3
+    with pytest.raises(TypeError):
+        materialize_transpose(A.T)
+    with pytest.raises(TypeError):
+        _num_zeroband_u(A)
+    with pytest.raises(TypeError):
+        _num_zeroband_l(A)
 
 
 def test_constructor_checks():
