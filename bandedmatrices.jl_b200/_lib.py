@@ -130,11 +130,13 @@ _handles: dict = {}
 
 
 def handle(device: int = 0) -> Handle:
-    """Process-wide default handle for ``device``, bound to torch's CURRENT stream at call time."""
+    """Handle for (``device``, torch's CURRENT stream): one handle per stream, because a handle owns scratch memory and
+    the device-side status block, which two streams must not share without ordering."""
     import torch
 
-    hd = _handles.get(device)
+    stream = int(torch.cuda.current_stream(device).cuda_stream)
+    hd = _handles.get((device, stream))
     if hd is None:
-        hd = _handles[device] = Handle(device)
-    hd.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        hd = _handles[(device, stream)] = Handle(device)
+        hd.set_stream(stream)
     return hd

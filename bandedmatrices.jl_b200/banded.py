@@ -183,6 +183,8 @@ def brand(m: int, n: int, l: int, u: int, seed: int | None = None, device=None) 
     g = torch.Generator(device=dev)
     if seed is not None:
         g.manual_seed(int(seed))
+    else:
+        g.seed()  # a fresh Generator starts from torch's fixed default seed: draw a new one, like the reference's global RNG
     data = torch.rand((n, max(0, l + u + 1)), dtype=torch.float64, device=dev, generator=g)
     return BandedMatrix(data, m, l, u)
 

@@ -202,6 +202,7 @@ gbtrf_update(i64 m, i64 n, int kl, int ku, double *__restrict__ ab, i64 ldab, co
 }
 
 int bmb_gbtrf_pipe(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv, i64 *Jdone);
+int bmb_gbtrf_strip(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv, i64 *Jdone);  // gbtrf_strip.cu
 
 int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv)
 {
@@ -221,7 +222,6 @@ int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, 
     const size_t smem_u = (size_t)TC * PR * sizeof(double);
     int rc = bmb_ensure_scratch(h, (size_t)NB * PR * sizeof(double) + 512);
     if (rc) return rc;
-    double *Lw = (double *)h->scratch;
     PanelState *st = (PanelState *)h->d_info;
     BMB_CUDA(h, cudaMemsetAsync(st, 0, sizeof(PanelState), h->stream));
     BMB_CUDA(h, cudaFuncSetAttribute(gbtrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
@@ -236,9 +236,18 @@ int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, 
     }
     // the bulk of the panels runs in the persistent pipelined kernel (gbtrf_pipe.cu); the stepwise kernels below
     // finish the last kl/NB + 1 panels (ragged rows) or do everything when the shape is not eligible
+    // Interchange-free matrices (verified on the fly) take the strip-resident kernel (gbtrf_strip.cu); it hands back 0
+    // columns, with AB as it was, when the shape is not eligible or an interchange turns out to be needed.
     i64 Jstart = 0;
-    rc = bmb_gbtrf_pipe(h, m, n, kl, ku, dAB, ldab, d_ipiv, &Jstart);
+    rc = bmb_gbtrf_strip(h, m, n, kl, ku, dAB, ldab, d_ipiv, &Jstart);
     if (rc) return rc;
+    if (Jstart == 0) {
+        rc = bmb_gbtrf_pipe(h, m, n, kl, ku, dAB, ldab, d_ipiv, &Jstart);
+        if (rc) return rc;
+    }
+    rc = bmb_ensure_scratch(h, (size_t)NB * PR * sizeof(double) + 512);
+    if (rc) return rc;
+    double *Lw = (double *)h->scratch;  // (taken here: the kernels above may have grown, i.e. moved, the scratch buffer)
     const unsigned ublocks = (unsigned)cdiv64(kv, TC);
     for (i64 J = Jstart; J < mn; J += NB) {
         const int nbw = (int)imin64(NB, n - J);
