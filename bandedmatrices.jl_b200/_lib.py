@@ -32,6 +32,7 @@ PROTOTYPES = {
     "bmb200_dfill_lmul": (C.c_int, [vp, dbl, vp, i64, i64, i64, i64]),
     "bmb200_dband_widen": (C.c_int, [vp, i64, i64, i64, vp, i64, vp, i64]),
     "bmb200_dgbtrf": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(C.c_int)]),
+    "bmb200_dgbtrf_from": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, C.POINTER(C.c_int)]),
     "bmb200_dgbtrs": (C.c_int, [vp, ch, i64, i64, i64, i64, vp, i64, vp, vp, i64]),
     "bmb200_dtbsv": (C.c_int, [vp, ch, ch, ch, i64, i64, vp, i64, vp, i64]),
     "bmb200_dtbmv": (C.c_int, [vp, ch, ch, ch, i64, i64, vp, i64, vp, i64]),

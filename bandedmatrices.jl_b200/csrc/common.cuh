@@ -55,6 +55,10 @@ struct bmb200_ctx {
     int *d_info = nullptr;     // [0]=info, [1]=ju, spare
     void *scratch = nullptr;   // grow-only workspace
     size_t scratch_bytes = 0;
+    void *backup = nullptr;    // grow-only copy of a band for the optimistic LU of an in-place call (gbtrf_strip.cu)
+    size_t backup_bytes = 0;
+    const double *lu_src = nullptr;  // set by bmb200_dgbtrf_from for the duration of the call: the un-widened source
+    int64_t lu_src_ld = 0;
     // pinned staging + second stream for the host-buffer entry points
     void *pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;

@@ -41,6 +41,7 @@ extern "C" int bmb200_destroy(bmb200_handle_t h)
     bmb200_halo_destroy(h);
     if (h->d_info) cudaFree(h->d_info);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->backup) cudaFree(h->backup);
     for (int i = 0; i < 2; ++i)
         if (h->pinned[i]) cudaFreeHost(h->pinned[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -180,6 +181,26 @@ extern "C" int bmb200_dband_widen(bmb200_handle_t h, int64_t n, int64_t l, int64
     band_widen_kernel<<<blocks, 256, 0, h->stream>>>(n, l, l + u + 1, dA, lda, dAB, ldab);
     BMB_LAUNCH_CHECK(h);
     return 0;
+}
+
+// ---- lu(A) = lu!(BandedMatrix{T}(A,(l,l+u))), src/banded/BandedLU.jl:106-111: widening copy + factorisation in one call.
+// Knowing the source lets the optimistic wide-band path (gbtrf_strip.cu) skip its device-side copy of the band: if an
+// interchange turns out to be needed it simply widens again. ----
+extern "C" int bmb200_dgbtrf_from(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, const double *dA, int64_t lda,
+                                  double *dAB, int64_t ldab, int64_t *d_ipiv, int *info)
+{
+    if (!h) return -1;
+    if (lda < kl + ku + 1) return -7;
+    if (ldab < 2 * kl + ku + 1) return -9;
+    if (info) *info = 0;
+    if (m == 0 || n == 0) return 0;
+    int rc = bmb200_dband_widen(h, n, kl, ku, dA, lda, dAB, ldab);
+    if (rc) return rc;
+    h->lu_src = dA;
+    h->lu_src_ld = lda;
+    rc = bmb200_dgbtrf(h, m, n, kl, ku, dAB, ldab, d_ipiv, info);
+    h->lu_src = nullptr;
+    return rc;
 }
 
 // ---- development hook (include/bmb200_internal.h): the only writer of the handle's tuning block ----

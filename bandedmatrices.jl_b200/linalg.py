@@ -452,8 +452,16 @@ def lu(A: BandedMatrix, check: bool = True) -> BandedLU:
         raise ValueError("invalid argument #1 to LAPACK call")  # gbtrf!(kl<0, ...) -> ArgumentError in the reference
     W = BandedMatrix.undef(A.shape, (l, l + u), device=A.data.device)
     hd = _h(A.data)
-    hd.check(hd.lib.bmb200_dband_widen(hd.h, A.n, l, u, vp(A.ptr), A.lda, vp(W.ptr), W.lda), "dband_widen")
-    return lu_(W, check)
+    mn = min(A.m, A.n)
+    d_ipiv = torch.empty(mn, dtype=torch.int64, device=A.data.device)
+    info = C.c_int(0)
+    rc = hd.lib.bmb200_dgbtrf_from(hd.h, A.m, A.n, l, u, vp(A.ptr), A.lda, vp(W.ptr), W.lda, vp(d_ipiv.data_ptr()), C.byref(info))
+    if rc < 0 and rc > -100:
+        raise ValueError(f"invalid argument #{-rc} to LAPACK call")
+    hd.check(rc, "dgbtrf_from")
+    if info.value > 0:
+        raise LAPACKException(info.value)  # gbtrf! -> chklapackerror, BandedLU.jl:98
+    return BandedLU(W, d_ipiv.cpu().numpy(), 0, d_ipiv)
 
 
 def ldiv_(F, B: torch.Tensor) -> torch.Tensor:

@@ -169,6 +169,13 @@ int bmb200_dband_axpby(bmb200_handle_t h, int64_t m, int64_t n, double alpha, in
                        int64_t ldx, double beta, int64_t yl, int64_t yu, const double *dY, int64_t ldy, int64_t zl,
                        int64_t zu, double *dZ, int64_t ldz);
 
+/* ---- lu(A): widening copy + factorisation in one call ------------------------------------------
+ * Replaces _lu, src/banded/BandedLU.jl:106-111 ( lu!(BandedMatrix{T}(A,(l,l+u))) ): dA is the (kl+ku+1) x n band storage of
+ * A, dAB receives the (2kl+ku+1) x n LU storage.  Same result as bmb200_dband_widen followed by bmb200_dgbtrf; giving the
+ * source lets the interchange-free wide-band path skip its own copy of the band.                                      */
+int bmb200_dgbtrf_from(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, const double *dA, int64_t lda,
+                       double *dAB, int64_t ldab, int64_t *d_ipiv, int *info);
+
 /* ---- host-buffer forms: what a Fortran-ABI caller with HOST arrays gets (bench.py "e2e") ----
  * Same semantics as the calls above; inputs are copied host->device in pipelined chunks, the
  * result is copied back, and the call returns after the result is in host memory.           */
