@@ -30,6 +30,7 @@ struct bmb_tuning {
     int gbmm_nt = 3;           // row tiles per work item (2 or 3)
     int gbmm_rw = 0;           // ring kernel warps per CTA (0 = by tile width)
     int gbtrf_nopipe = 0;      // 1 disables the pipelined wide-band LU
+    int gbtrf_nomw = 0;        // 1 disables the multi-warp narrow-band LU (gbtrf_mw.cu)
     int gbtrf_nostrip = 0;     // 1 disables the strip-resident interchange-free LU
     long long pipe_maxpanels = 0;  // > 0 caps the panels the pipelined LU takes
     int pipe_nospec = 0;       // 1 disables optimistic diagonal pivoting

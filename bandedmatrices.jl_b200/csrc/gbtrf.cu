@@ -18,6 +18,7 @@
 
 int bmb_gbtrf_blocked(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv);
 int bmb_gbtrf_reg(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv);  // gbtrf_reg.cu
+int bmb_gbtrf_mw(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double *dAB, i64 ldab, i64 *d_ipiv);   // gbtrf_mw.cu
 
 #define GBTRF_PF 12
 
@@ -179,8 +180,9 @@ extern "C" int bmb200_dgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl
     const int nslot = (int)(kv + GBTRF_PF + 2);
     const size_t smem = ((size_t)nslot * ldw + 2 * (kv + 1) + (kl + 1)) * sizeof(double);
     int rc;
-    if (kl <= 31 && kv + 1 <= 33) {  // software-pipelined register kernel (gbtrf_reg.cu)
-        rc = bmb_gbtrf_reg(h, m, n, kl, ku, dAB, ldab, d_ipiv);
+    if (kl <= 31 && kv + 1 <= 33) {  // register-window kernels: several warps (gbtrf_mw.cu), else one (gbtrf_reg.cu)
+        rc = h->tune.gbtrf_nomw ? 1 : bmb_gbtrf_mw(h, m, n, kl, ku, dAB, ldab, d_ipiv);
+        if (rc == 1) rc = bmb_gbtrf_reg(h, m, n, kl, ku, dAB, ldab, d_ipiv);
         if (rc) return rc;
     } else if (smem <= 220 * 1024) {
         BMB_CUDA(h, cudaFuncSetAttribute(gbtrf_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

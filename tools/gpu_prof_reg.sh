@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 exec > gpurun_out/prof_reg.log 2>&1
 set -x
 NCU="ncu --clock-control none --set full --import-source on"
-timeout 600 $NCU -k regex:gbtrf_reg -s 1 -c 1 -o gpurun_out/p_reg -f python tools/prof_case.py lu 131072 > /dev/null 2>&1
+timeout 600 $NCU -k regex:gbtrf_mw -s 1 -c 1 -o gpurun_out/p_reg -f python tools/prof_case.py lu 131072 > /dev/null 2>&1
 ncu -i gpurun_out/p_reg.ncu-rep --page raw --csv > gpurun_out/reg_raw.csv 2>/dev/null
 ncu -i gpurun_out/p_reg.ncu-rep --page source --csv > gpurun_out/reg_source.csv 2>/dev/null
 rm -f gpurun_out/p_reg.ncu-rep
