@@ -352,7 +352,7 @@ def run_c5(bm, L, hbm_peak, N=1024):
                 "flops": flops,
                 "roofline": {"bound": "tensor", "achieved": round(flops / t_f / 1e9, 3), "peak": tpeak, "unit": "TFLOP/s (FP64)",
                              "frac": round(flops / t_f / 1e9 / tpeak, 4), "traffic": None, "peak_source": tsrc,
-                             "kernel": "gbtrf_pipe_kernel (chain CTA + DMMA update CTAs)"},
+                             "kernel": "gbtrf_strip_kernel (strip-resident LU: diagonal-block chain + DMMA strip updates, verified diagonal pivots)"},
                 "parity": par})
     del A, F, x, r, rhs
     torch.cuda.empty_cache()
