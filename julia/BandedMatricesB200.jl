@@ -113,6 +113,30 @@ function LAPACK.gbtrf!(kl::Integer, ku::Integer, m::Integer, AB::DMat)
     AB, ipiv
 end
 
+# ---- lu(A): widening copy + factorisation in one call (src/banded/BandedLU.jl:106-111) ----
+function BandedMatrices._lu(::BandedMatrices.BandedColumns, axes, A::DBanded, pivot = Val(true); check::Bool = true)
+    m, n = size(A);  l, u = bandwidths(A)
+    W = BandedMatrix{Float64}(undef, (m, n), (l, l + u))          # B200Array container (similar(A) in the real glue)
+    AB = bandeddata(W);  D = bandeddata(A)
+    dip = B200Array{Int64,1}(undef, (min(m, n),));  info = Ref{Cint}(0)
+    chk(ccall((:bmb200_dgbtrf_from, libbmb200), Cint,
+              (Handle, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Ref{Cint}),
+              handle(), m, n, l, u, D, stride(D, 2), AB, stride(AB, 2), dip, info), "dgbtrf_from")
+    check && LAPACK.chklapackerror(BlasInt(info[]))
+    BandedMatrices.BandedLU{Float64,typeof(W)}(W, Array(dip), BlasInt(info[]))
+end
+
+# ---- dense x banded (src/generic/matmul.jl:258-271): one launch instead of one strided gbmv per row of C ----
+function ArrayLayouts.materialize!(M::ArrayLayouts.MatMulMatAdd{<:Any,<:BandedMatrices.BandedColumns,<:Any,Float64,<:DMat,<:DBanded,<:DMat})
+    α, A, B, β, C = M.α, M.A, M.B, M.β, M.C
+    P = bandeddata(B)
+    chk(ccall((:bmb200_dgbmm_db, libbmb200), Cint,
+              (Handle, UInt8, Int64, Int64, Int64, Int64, Int64, Float64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Int64),
+              handle(), 'N', size(A, 1), size(B, 1), size(B, 2), bandwidth(B, 1), bandwidth(B, 2), α, A, stride(A, 2), P, stride(P, 2),
+              β, C, stride(C, 2)), "dgbmm_db")
+    C
+end
+
 function LAPACK.gbtrs!(trans::AbstractChar, kl::Integer, ku::Integer, m::Integer, AB::DMat, ipiv::Vector{BlasInt}, B::Union{DVec,DMat})
     dip = get!(() -> B200Array(ipiv), DEVICE_IPIV, ipiv)
     chk(ccall((:bmb200_dgbtrs, libbmb200), Cint, (Handle, UInt8, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}, Int64),

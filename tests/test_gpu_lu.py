@@ -364,3 +364,61 @@ def test_slot_solve_sparse_rhs_and_nonfinite(bm, oracle_c, rng):
     got = X.cpu().numpy()
     assert np.array_equal(got, ref, equal_nan=True)
     assert np.array_equal(np.signbit(got[:, 5]), np.signbit(ref[:, 5]))  # signed zeros survive too
+
+
+# ---- round 2: strip-resident wide-band LU (gbtrf_strip.cu) and multi-warp narrow LU (gbtrf_mw.cu) ----
+@pytest.mark.parametrize("shape", [(3000, 200, 180), (2100, 64, 257), (4000, 513, 48)])
+def test_strip_lu_in_place_entry_uses_device_copy(bm, oracle_c, rng, shape):
+    """lu!(A) on an already widened matrix (bmb200_dgbtrf without the source): the optimistic strip kernel keeps a
+    device-side copy of the band; pivots = 1:n and factors bit-identical to DGBTF2.  Then the same with a weak diagonal:
+    the copy is restored and the general path gives DGBTF2's pivots and bits."""
+    n, l, u = shape
+    A = brand(rng, n, n, l, u)
+    A.data[u, :] += 2.0 * (l + u + 1)
+    for weak in (None, n // 2 + 3):
+        if weak is not None:
+            A.data[u, weak] = 1e-3
+        ab, ipiv, info = lu(oracle_c, A)
+        W = bm.BandedMatrix.zeros((n, n), (l, l + u))
+        W.data[:, l:] = torch.as_tensor(np.ascontiguousarray(A.data.T)).cuda()
+        F = bm.lu_(W)
+        assert np.array_equal(F.ipiv, ipiv), weak
+        assert np.array_equal(F.factors.banddata_host(), ab), weak
+        assert (weak is None) == bool((ipiv == np.arange(1, n + 1)).all())
+
+
+def test_wide_band_nan_entry_no_cuda_error(bm, rng):
+    """A NaN inside a dominant wide band: the strip kernel treats it as a violation, the general path factors on; the
+    call must return (NaN in the factors), the pivots must stay in range, and the context must stay usable."""
+    n, l, u = 2500, 130, 120
+    A = brand(rng, n, n, l, u)
+    A.data[u, :] += 2.0 * (l + u + 1)
+    A.data[u + 7, 900] = np.nan
+    F = bm.lu(up(bm, A))
+    assert F.ipiv.min() >= 1 and F.ipiv.max() <= n
+    assert np.isnan(F.factors.banddata_host()).any()
+    B = brand(rng, 500, 500, 4, 3)          # the handle still works
+    ab, ipiv, info = lu(oracle.backend("C"), B)
+    F2 = bm.lu(up(bm, B))
+    assert np.array_equal(F2.ipiv, ipiv) and np.array_equal(F2.factors.banddata_host(), ab)
+
+
+@pytest.mark.parametrize("shape", [(900, 1300, 16, 16), (1300, 900, 16, 16), (40, 40, 16, 16), (17, 64, 5, 2), (3000, 3000, 31, 1),
+                                   (3000, 3000, 1, 31), (2000, 2000, 2, 1), (515, 515, 9, 6), (8, 8, 4, 3)])
+def test_multi_warp_narrow_lu_matches_single_warp_and_oracle(bm, oracle_c, rng, shape):
+    """gbtrf_mw.cu (chain warp + far warps) against the oracle and against the single-warp kernel it replaces, rectangular and
+    tiny shapes included (entering rows that do not exist, U rows cut by the matrix edge)."""
+    m, n, l, u = shape
+    A = brand(rng, m, n, l, u)
+    ab, ipiv, info = lu(oracle_c, A)
+    hd = bm.handle(0)
+    F = bm.lu(up(bm, A))
+    assert np.array_equal(F.ipiv, ipiv)
+    assert np.array_equal(F.factors.banddata_host(), ab)
+    hd.tune("gbtrf_nomw", 1)
+    try:
+        F1 = bm.lu(up(bm, A))
+    finally:
+        hd.tune("reset", 0)
+    assert np.array_equal(F1.ipiv, F.ipiv)
+    assert np.array_equal(F1.factors.banddata_host(), F.factors.banddata_host())

@@ -1,8 +1,14 @@
 #!/bin/bash
-# full parity run + extras bench
+# full GPU pass: parity tests, smoke, default bench line
 mkdir -p gpurun_out
-exec > gpurun_out/full.log 2>&1
-set -x
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -2
-timeout 900 python bench.py --extras --no-e2e --no-cpu --steps 5 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 1400 gpurun_out/bench_full.json; tail -3 gpurun_out/bench_full.err
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/bench.json"))
+print("value", d["value"], "e2e", d["e2e"]["value"], "frac", d["roofline"]["frac"])
+for k, v in d["configs"].items():
+    print(k, {kk: vv for kk, vv in v.items() if kk.endswith("_ms") or kk.endswith("_us") or kk in ("ms", "lu_ms_incl_widen", "solve_ms", "GFLOPs", "lu_TFLOPs")}, v.get("parity"))
+PY
