@@ -84,6 +84,11 @@ gbmv_n_systolic_sharded(i64 m, i64 n, int kl, int ku, double alpha, const double
                         double beta, double *__restrict__ y, i64 total_sets, i64 sets_per_run, i64 num_runs,
                         HaloBox left, HaloBox right, int push_l, int push_r, int par)
 {
+    // Programmatic dependent launch: the NEXT product in the stream may be launched now, so that its blocks take the SMs
+    // this grid's blocks leave one by one (launch latency and block dispatch hide behind this grid's tail); its blocks
+    // wait in griddepcontrol.wait -- before touching memory -- until this grid has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (blockIdx.x == 0 && threadIdx.x < 32) {  // push first, then behave like any other warp
         const int lane = threadIdx.x;
         if (left.base && lane < push_l) left.from_right(par)[lane] = xs.x[lane];                     // my first ku entries
@@ -160,9 +165,18 @@ static int launch_sharded(bmb200_ctx *h, i64 ms, i64 ns, i64 kls, i64 kus, doubl
         BMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, gbmv_n_systolic_sharded<W, LDV>, threads, 0));
     const int per_sm = per_sm_cached;
     const SystolicPlan p = systolic_plan(ms, kus, h->sm_count, per_sm, threads);
-    gbmv_n_systolic_sharded<W, LDV><<<(unsigned)p.blocks, threads, 0, h->stream>>>(
-        ms, ns, (int)kls, (int)kus, alpha, dA, lda, xs, beta, dy, p.total_sets, p.sets_per_run, p.num_runs, L, R, push_l,
-        push_r, par);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.blocks);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BMB_CUDA(h, cudaLaunchKernelEx(&cfg, gbmv_n_systolic_sharded<W, LDV>, ms, ns, (int)kls, (int)kus, alpha, dA, lda, xs, beta, dy,
+                                   p.total_sets, p.sets_per_run, p.num_runs, L, R, push_l, push_r, par));
     BMB_LAUNCH_CHECK(h);
     return 0;
 }
