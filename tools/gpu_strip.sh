@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 exec > gpurun_out/strip2.log 2>&1
-timeout 600 python -m pytest tests/test_gpu_lu.py -m gpu -x -q -k "wide or laplacian" 2>&1 | tail -5
-timeout 300 python - <<'PY'
+timeout 240 python -m pytest tests/test_gpu_lu.py -m gpu -x -q -k "wide or laplacian" 2>&1 | tail -5
+timeout 150 python - <<'PY'
 import sys, torch
 sys.path.insert(0, ".")
 import bandedmatrices_b200 as bm
