@@ -37,6 +37,8 @@ PROTOTYPES = {
     "bmb200_dtbsv": (C.c_int, [vp, ch, ch, ch, i64, i64, vp, i64, vp, i64]),
     "bmb200_dtbmv": (C.c_int, [vp, ch, ch, ch, i64, i64, vp, i64, vp, i64]),
     "bmb200_dsbmv": (C.c_int, [vp, ch, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
+    "bmb200_dpbtrf": (C.c_int, [vp, ch, i64, i64, vp, i64, C.POINTER(C.c_int)]),
+    "bmb200_dpbtrs": (C.c_int, [vp, ch, i64, i64, i64, vp, i64, vp, i64]),
     "bmb200_dband_axpy": (C.c_int, [vp, i64, i64, dbl, i64, i64, vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64)]),
     "bmb200_dband_copy": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64)]),
     "bmb200_dband_lmul_block": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i64, dbl]),

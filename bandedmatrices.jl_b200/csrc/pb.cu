@@ -1,0 +1,570 @@
+// pb.cu -- banded Cholesky on the device: pbtrf! / pbtrs! of the reference (src/lapack.jl:268-332), reached from
+// cholesky(Symmetric(::BandedMatrix)) (banded_chol!, src/symbanded/BandedCholesky.jl:2-13) and its ldiv! (:72-80).
+// SURVEY.md 8(f) rank 3, the factorisation half.
+//
+// Storage (LAPACK symmetric band): 'U': A[i,k] (i <= k) at ab[(kd + i - k) + k*ldab]; 'L': A[i,k] (i >= k) at ab[(i - k) + k*ldab].
+// Both are ONE upper factor U (A = U^T U; for 'L' the stored factor is L = U^T) addressed with two strides:
+//     U(i,k) = p[i*si + k*sk]      'U': p = ab + kd, si = 1, sk = ldab-1        'L': p = ab, si = ldab-1, sk = 1
+// so every kernel below is written once, on U(i,k), i <= k <= i + kd.
+//
+// kd <= 64 -- DPBTF2, the unblocked algorithm DPBTRF runs there (ILAENV gives NB = 1 for kd <= 64): per column j
+//     d = sqrt(A[j,j]); row j *= 1/d (DSCAL by the reciprocal); trailing triangle -= x x^T, one FMA per entry with t = -x[c]
+//     rounded first (DSYR as OpenBLAS runs it).  `pbtf2_window` keeps the kd+1 live columns in a shared-memory ring fed by
+//     cp.async, every thread recomputes the reciprocal itself (no broadcast step), one barrier per column.  Each entry receives
+//     its updates in ascending j exactly as the CPU does: factors are BIT-IDENTICAL to OpenBLAS dpbtrf_.
+// kd > 64 -- blocked right-looking (the structure of DPBTRF, NB = 64 here): per panel of NB columns
+//     K1 `pbtf2_window` on the NB x NB diagonal block, K2 `pb_trsm` U12 = U11^{-T} A12 (one thread per column of A12, the
+//     substitution kept in registers), K3 `pb_syrk` A22 -= U12^T U12 on the kd x kd window (64 x 64 tiles, 4 x 4 register tiles
+//     of FP64 FMAs -- on B200 the FP64 FMA pipe and DMMA have the same peak, profiles/fp64_peaks_r1.json).  The three kernels
+//     of a panel read the panel index from a device counter, so a CUDA graph of PB_GRAPH_PANELS panels is captured once per
+//     handle and replayed; panels past the end are no-ops.  DPBTRF's DGEMM/DSYRK order is unspecified: compared to
+//     OpenBLAS at 1e-13 * cond-ish tolerances and through ||U^T U - A||.
+// pbtrs -- DPBTRS = two DTBSV sweeps per right-hand side ('U': U^T then U; 'L': L then L^T), run for ALL right-hand sides at
+//     once (cluster pipeline of gbtrs_cluster.cu for the 'N' sweep, one chain block per right-hand side for the 'T' sweep).
+#include "common.cuh"
+
+#define PB_NB 64
+#define PB_PFD 8
+#define PB_GRAPH_PANELS 128
+#define PB_SP 72  // doubles per staged row / column of a U12 slab (pitches 68 and 72 both fit)
+
+int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
+int bmb_tbsv_t_multi(bmb200_ctx *h, int up, int unit, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);      // tb.cu
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(double *smem_dst, const double *gsrc, bool valid)  // !valid: writes 0.0, reads nothing
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 1/sqrt(a) to about an ulp: hardware seed + two Newton steps (~85 cycles against ~270 for sqrt followed by a divide)
+__device__ __forceinline__ double pb_rsqrt(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = y * fma(-(h * y), y, 1.5);
+    y = y * fma(-(h * y), y, 1.5);
+    return y;
+}
+
+// d_state: [0] = info (0 ok, > 0 first non-positive pivot, 1-based), [1] = panel counter of the blocked path.
+// The kd+1 live columns sit in a shared-memory ring: entry U(k-d, k) at win[((k*P + d) & MASK)], P and the slot count powers of
+// two, so one add and one mask address anything relative to the current column.  A thread owns up to E entries (r, c),
+// 1 <= r <= c <= kd, of the trailing triangle RELATIVE to the current column j (offsets precomputed once, enumerated by
+// ascending c so that the live entries of a shrinking triangle are a prefix).  One step: every thread loads the pivot, its
+// entries and their two row-j factors, takes the square root / reciprocal itself (no broadcast), updates, one barrier.  The
+// single warp per scheduler hides nothing, so the step is kept to the instructions the dependency chain needs.
+template <int NT, int E>
+__global__ void __launch_bounds__(NT)
+pbtf2_window(i64 n_total, int kd_total, int blocked, i64 si, i64 sk, double *__restrict__ p0, int ring, int P, int *__restrict__ d_state,
+             double *__restrict__ d_rdiag, long long *__restrict__ stats)
+{
+    extern __shared__ double win[];
+    __shared__ int s_panel;
+    long long tk0 = 0, tk1 = 0, tk2 = 0, acc0 = 0, acc1 = 0, acc2 = 0;  // development aid (tuning key pipe_stats)
+    if (d_state[0] != 0) return;
+    i64 j0 = 0, n = n_total;
+    int kd = kd_total;
+    if (blocked) {  // the NB x NB diagonal block of the next panel
+        if (threadIdx.x == 0) { s_panel = d_state[1] + 1; d_state[1] = s_panel; }
+        __syncthreads();
+        j0 = (i64)s_panel * PB_NB;
+        if (j0 >= n_total) return;
+        n = imin64_d(PB_NB, n_total - j0);
+        kd = kd_total < PB_NB - 1 ? kd_total : PB_NB - 1;
+    }
+    double *p = p0 + j0 * (si + sk);  // U(j0, j0)
+    const int MASK = ring * P - 1, tid = threadIdx.x;
+    // entry offsets relative to column j: entry (r,c) -> c*P + (c-r); its factors S(j,j+r) -> r*P + r, S(j,j+c) -> c*P + c
+    int oe[E], oxr[E], oxc[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int e = tid + m * NT;
+        int c = 1;
+        while (c * (c + 1) / 2 <= e) ++c;
+        const int r = e - c * (c - 1) / 2 + 1;
+        oe[m] = c * P + (c - r);
+        oxr[m] = r * P + r;
+        oxc[m] = c * P + c;
+    }
+    const i64 diag = si + sk;
+    const i64 tsk = (i64)tid * sk, tsi = (i64)tid * si;
+    auto fetch = [&](i64 k) {          // column k of the block -> its ring slot
+        if (k < n) {
+            const int dmax = k < kd ? (int)k : kd;
+            const int base = (int)((k * P) & MASK);
+            const double *src = p + k * diag;
+            for (int d = tid; d <= dmax; d += NT) cp_async8(win + ((base + d) & MASK), src - (i64)d * si);
+        }
+        cp_async_commit();
+    };
+    for (i64 k = 0; k < kd + PB_PFD; ++k) fetch(k);
+    cp_async_wait<0>();
+    __syncthreads();
+    int jP = 0;
+    double *rowp = p;  // U(j, j)
+    for (i64 j = 0; j < n; ++j, jP = (jP + P) & MASK, rowp += diag) {
+        if (stats) tk0 = clock64();
+        const int kn = (int)imin64_d(kd, n - 1 - j);
+        const int cnt = kn * (kn + 1) / 2;
+        // everything that does not depend on the pivot is loaded first
+        const double ajj = win[jP];
+        double ev[E], xr[E], xc[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const bool ok = tid + m * NT < cnt;
+            ev[m] = ok ? win[(oe[m] + jP) & MASK] : 0.0;
+            xr[m] = ok ? win[(oxr[m] + jP) & MASK] : 0.0;
+            xc[m] = ok ? win[(oxc[m] + jP) & MASK] : 0.0;
+        }
+        double rowv = 0.0;
+        if (NT > 64 || tid <= kn) rowv = (tid <= kn) ? win[(tid * P + tid + jP) & MASK] : 0.0;
+        if (ajj <= 0.0) {  // not positive definite: DPBTF2 stops here with info = j+1 and the trailing window as updated so far
+            for (int c = 0; c <= kn; ++c)
+                for (int d = tid; d <= c; d += NT) p[(j + c - d) * si + (j + c) * sk] = win[(int)(((j + c) * P + d) & MASK)];
+            if (tid == 0) d_state[0] = (int)(j0 + j + 1);
+            cp_async_wait<0>();
+            return;
+        }
+        double dj, rinv;
+        if (blocked) {  // the blocked path owes rounding-level agreement only: one reciprocal square root instead of sqrt + divide
+            rinv = pb_rsqrt(ajj);
+            dj = __dmul_rn(ajj, rinv);
+            if (tid == 0) d_rdiag[j] = rinv;
+        } else {
+            dj = sqrt(ajj);
+            rinv = 1.0 / dj;
+        }
+        if (stats) { if (rinv == 123.456) d_state[3] = 1; tk1 = clock64(); }
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            if (tid + m * NT < cnt) {
+                const double t = -__dmul_rn(xc[m], rinv);
+                if (t != 0.0) win[(oe[m] + jP) & MASK] = fma(t, __dmul_rn(xr[m], rinv), ev[m]);  // OpenBLAS dsyr skips zero entries of x
+            }
+        }
+        if (tid <= kn) rowp[tsk] = tid == 0 ? dj : __dmul_rn(rowv, rinv);  // row j is final: U(j, j+tid)
+        fetch(j + kd + PB_PFD);
+        cp_async_wait<PB_PFD - 1>();
+        __syncthreads();
+        if (stats) { tk2 = clock64(); acc0 += tk1 - tk0; acc1 += tk2 - tk1; }
+    }
+    cp_async_wait<0>();
+    (void)tsi; (void)acc2;
+    if (stats && tid == 0) {
+        atomicAdd((unsigned long long *)stats + 0, (unsigned long long)acc0);
+        atomicAdd((unsigned long long *)stats + 1, (unsigned long long)acc1);
+        atomicAdd((unsigned long long *)stats + 4, (unsigned long long)n);
+    }
+}
+
+// K1 of the blocked path: Cholesky of the NB x NB diagonal block, REGISTER resident.  Thread (a, b) = (tid / 16, tid % 16)
+// owns the 4 x 4 patch rows 4a.., columns 4b.. (patches below the diagonal idle).  Step j = 4*jb + u (u unrolled, so every
+// register index is static): the 16 lanes with a == jb sit in one warp -- the pivot comes by one shuffle from the diagonal
+// lane, every lane takes the reciprocal square root itself, scales its part of row j (the other half-warp multiplies by 1) and
+// posts it in shared memory; one barrier; every patch right/below subtracts x_r x_c.  Per step the dependency chain is
+// shuffle + rsqrt + multiply + one shared-memory round trip + FMA (tools/fp64_issue.cu: ~30 + 72 + 10 + ~210 cycles); shared
+// memory is addressed through precomputed 32-bit addresses and nothing inside the step touches global or constant memory.
+// The reciprocal diagonal goes to d_rdiag for K2.
+__device__ __forceinline__ void pb_lds2(unsigned addr, double &x, double &y) { asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr)); }
+__device__ __forceinline__ void pb_sts2(unsigned addr, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(x), "d"(y) : "memory"); }
+
+__global__ void __launch_bounds__(256)
+pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, double *__restrict__ d_rdiag)
+{
+    __shared__ __align__(16) double xs[2][PB_NB];
+    __shared__ double rd[PB_NB];
+    __shared__ int s_panel, s_fail;
+    if (d_state[0] != 0) return;
+    if (threadIdx.x == 0) { s_panel = d_state[1] + 1; d_state[1] = s_panel; s_fail = 0; }
+    __syncthreads();
+    const i64 j0 = (i64)s_panel * PB_NB;
+    if (j0 >= n_total) return;
+    const int nbl = (int)imin64_d(PB_NB, n_total - j0);
+    double *p = p0 + j0 * (si + sk);  // U(j0, j0)
+    // the compiler otherwise re-reads %tid and rebuilds the shared-window base (S2R / S2UR, tens of cycles each) inside every
+    // step, right on the dependency chain: read them once through volatile asm so that they have to stay in registers
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int a = tid >> 4, b = tid & 15, lane = tid & 31, warp = tid >> 5;
+    const bool upper = b >= a;
+    double v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int r = 4 * a + u, c = 4 * b + w;
+            v[u][w] = (upper && r <= c && c < nbl) ? p[(i64)r * si + (i64)c * sk] : ((r == c) ? 1.0 : 0.0);
+        }
+    unsigned xs0 = (unsigned)__cvta_generic_to_shared(&xs[0][0]);
+    unsigned rd0 = (unsigned)__cvta_generic_to_shared(&rd[0]);
+    unsigned fl0 = (unsigned)__cvta_generic_to_shared(&s_fail);
+    asm volatile("mov.u32 %0, %0;" : "+r"(xs0));
+    asm volatile("mov.u32 %0, %0;" : "+r"(rd0));
+    asm volatile("mov.u32 %0, %0;" : "+r"(fl0));
+    unsigned xr_a = xs0 + 32u * a, xc_a = xs0 + 32u * b;  // this patch's row / column factors inside one x buffer
+    asm volatile("mov.u32 %0, %0;" : "+r"(xr_a));
+    asm volatile("mov.u32 %0, %0;" : "+r"(xc_a));
+    int failed = 0;
+#ifdef PB_DEBUG_TIMING
+    long long dbg_c0 = clock64(), dbg_t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+#endif
+#pragma unroll 1
+    for (int jb = 0; jb < PB_NB / 4; ++jb) {
+        const bool inwarp = warp == (jb >> 1);          // this warp holds rows 4jb..4jb+3
+        const bool rowgrp = a == jb && upper;           // this thread holds a piece of them
+        const int dlane = ((jb & 1) << 4) + jb;         // lane of the diagonal patch (a == b == jb)
+        const bool live = upper && a >= jb;
+        const bool bgt = b > jb, bge = b >= jb;         // column 4b+w against column j = 4jb+u: > iff bgt or (b == jb and w > u)
+        const bool isdiag = rowgrp && b == jb;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = 4 * jb + u;
+            if (j < nbl) {  // block-uniform
+                const unsigned buf = (unsigned)(u & 1) * (PB_NB * 8u);
+                if (inwarp) {
+                    const double ajj = __shfl_sync(0xffffffffu, v[u][u], dlane);
+                    const bool ok = ajj > 0.0;
+                    const double rinv = pb_rsqrt(ajj);
+                    const double sc = (rowgrp && ok) ? rinv : 1.0;
+                    double xv[4];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const double scaled = __dmul_rn(v[u][w], sc);
+                        v[u][w] = scaled;
+                        xv[w] = ((w > u) ? bge : bgt) ? scaled : 0.0;
+                    }
+                    if (isdiag && ok) v[u][u] = __dmul_rn(ajj, rinv);
+                    if (rowgrp) { pb_sts2(xc_a + buf, xv[0], xv[1]); pb_sts2(xc_a + buf + 16u, xv[2], xv[3]); }
+                    if (lane == dlane) {
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(rd0 + 8u * j), "d"(rinv) : "memory");
+                        if (!ok) asm volatile("st.shared.u32 [%0], %1;" ::"r"(fl0), "r"(j + 1) : "memory");
+                    }
+                }
+                __syncthreads();
+                int f;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(fl0));
+                double xr[4], xc[4];
+                pb_lds2(xr_a + buf, xr[0], xr[1]);
+                pb_lds2(xr_a + buf + 16u, xr[2], xr[3]);
+                pb_lds2(xc_a + buf, xc[0], xc[1]);
+                pb_lds2(xc_a + buf + 16u, xc[2], xc[3]);
+                if (f) { failed = f; break; }  // not positive definite: stop with the block as updated so far (DPBTF2)
+                if (live) {
+                    // rows below j of this patch: all four for a > jb; in the row group itself x[r] = 0 for r <= j makes the finished
+                    // rows a no-op, so one unpredicated rank-1 update serves both
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) v[uu][w] = fma(-xr[uu], xc[w], v[uu][w]);
+                }
+            }
+        }
+        if (failed) break;
+    }
+#ifdef PB_DEBUG_TIMING
+    if (tid == 0 && s_panel == 10) {
+        long long dbg_t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
+        printf("pb_potf2_reg panel 10: step loop %lld cycles, %lld ns\n", clock64() - dbg_c0, dbg_t1 - dbg_t0);
+    }
+#endif
+    if (failed && tid == 0) d_state[0] = (int)(j0 + failed);
+    if (tid < nbl) d_rdiag[tid] = rd[tid];
+    // the factor (also the partially updated block after a failure, as DPBTF2 leaves it)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int r = 4 * a + u, c = 4 * b + w;
+            if (upper && r <= c && c < nbl) p[(i64)r * si + (i64)c * sk] = v[u][w];
+        }
+}
+
+// K2: U12 = U11^{-T} A12.  Rows = the panel's NB rows j0..j0+nbl-1, columns = the kd columns right of the panel.  PB_TPC
+// lanes per column (lane q holds rows q, q+TPC, ...: NB/TPC registers; many threads with few FMAs each, because a warp issues
+// FP64 FMAs slowly and the work is only a few MFLOP), right-looking substitution: u_i = a_i / U11(i,i) is
+// broadcast by a shuffle, every lane updates its rows t > i.  U11 sits in shared memory with its diagonal moved to a
+// reciprocal array and zeros on and below the diagonal, so the update needs no predicate.  A column's entries above the band
+// (row i reaches column i+kd only) are not stored and count as zero.
+#define PB_TPC 16
+__global__ void __launch_bounds__(256)
+pb_trsm(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__restrict__ d_state, const double *__restrict__ d_rdiag)
+{
+    __shared__ double u11[PB_NB * PB_NB];  // U11(i,t) at [i*NB + t] for t > i, else 0
+    __shared__ double rdiag[PB_NB];
+    if (d_state[0] != 0) return;
+    const i64 j0 = (i64)d_state[1] * PB_NB;
+    if (j0 >= n) return;
+    const int nbl = (int)imin64_d(PB_NB, n - j0);
+    const i64 c1 = j0 + nbl;                       // first column right of the panel
+    const i64 ncols = imin64_d(kd, n - c1);        // columns of A12 (row j0+nbl-1 reaches c1-1+kd)
+    if (ncols <= 0) return;
+    double *p = p0;
+    for (int e = threadIdx.x; e < PB_NB * PB_NB; e += blockDim.x) {  // all copies in flight at once
+        int i, t;
+        if (si == 1) { i = e % PB_NB; t = e / PB_NB; } else { t = e % PB_NB; i = e / PB_NB; }
+        const bool ok = i < nbl && t < nbl && i < t;
+        cp_async8_zfill(u11 + i * PB_NB + t, p + (j0 + (ok ? i : 0)) * si + (j0 + (ok ? t : 0)) * sk, ok);
+    }
+    if (threadIdx.x < PB_NB) cp_async8_zfill(rdiag + threadIdx.x, d_rdiag + threadIdx.x, (int)threadIdx.x < nbl);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int q = threadIdx.x % PB_TPC;
+    const i64 c = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / PB_TPC;
+    const bool live = c < ncols;  // dead lanes keep shuffling
+    const i64 k = c1 + (live ? c : 0);
+    // first stored panel row of column k: k <= (j0+i) + kd  =>  i >= k - kd - j0
+    const int i0 = (int)imax64_d(0, k - kd - j0);
+    double a[PB_NB / PB_TPC];
+#pragma unroll
+    for (int s = 0; s < PB_NB / PB_TPC; ++s) {
+        const int i = s * PB_TPC + q;
+        a[s] = (live && i >= i0 && i < nbl) ? p[(j0 + i) * si + k * sk] : 0.0;
+    }
+    const unsigned lane = threadIdx.x & 31u, base = lane & ~(unsigned)(PB_TPC - 1);
+#pragma unroll
+    for (int i = 0; i < PB_NB; ++i) {
+        const double mine = __dmul_rn(a[i / PB_TPC], rdiag[i]);
+        const double ui = __shfl_sync(0xffffffffu, mine, base + (i % PB_TPC));
+        if (q == i % PB_TPC) a[i / PB_TPC] = ui;
+        const double *urow = u11 + i * PB_NB + q;
+#pragma unroll
+        for (int s = i / PB_TPC; s < PB_NB / PB_TPC; ++s) a[s] = fma(-urow[s * PB_TPC], ui, a[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < PB_NB / PB_TPC; ++s) {
+        const int i = s * PB_TPC + q;
+        if (live && i >= i0 && i < nbl) p[(j0 + i) * si + k * sk] = a[s];
+    }
+}
+
+// K3: A22(r,c) -= sum_i U12(i,r) U12(i,c) for r <= c inside the window of kd columns right of the panel.  One CTA per 64 x 64
+// tile of the upper triangle; the two 64-column slabs of U12 are staged in shared memory (zero outside the band / the matrix)
+// and the product runs on the FP64 tensor cores (DMMA.8x8x4): with one CTA per SM there are only two warps per scheduler,
+// which saturates the tensor pipe but leaves the FP64 FMA pipe at a fraction of its rate (measured: 16 FMAs per thread took
+// ~700 cycles in the first version of this kernel).  Warp w owns the eight 8 x 8 tiles of tile row w: one A fragment and eight
+// B fragments per k-step of 4.  blockIdx.x enumerates the tiles (tr <= tc) of the largest window; tiles past the actual window
+// return.  Staged element (panel row i, window column x) sits at s[i*SI + x*SX]: the dimension that is contiguous in global
+// memory is contiguous in shared memory, and the other pitch is chosen so that a fragment load (4 values of i x 8 values of x)
+// touches every bank pair exactly twice (the minimum for 32 doubles): SX = 68 = 4 mod 16 ('U'), SI = 72 = 8 mod 16 ('L').
+__device__ __forceinline__ void pb_dmma884(double &d0, double &d1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256)
+pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__restrict__ d_state, int ntile1d)
+{
+    extern __shared__ __align__(16) double pb_sm[];
+    double *sr = pb_sm, *sc = pb_sm + PB_NB * PB_SP;
+    if (d_state[0] != 0) return;
+    const i64 j0 = (i64)d_state[1] * PB_NB;
+    if (j0 >= n) return;
+    const int nbl = (int)imin64_d(PB_NB, n - j0);
+    const i64 c1 = j0 + nbl;
+    const i64 ncols = imin64_d(kd, n - c1);
+    if (ncols <= 0) return;
+    // tile index -> (tr, tc), tr <= tc < ntile1d
+    int tc = 0, rem = blockIdx.x;
+    while (rem > tc) { rem -= tc + 1; ++tc; }
+    const int tr = rem;
+    if ((i64)tc * 64 >= ncols) return;
+    double *p = p0;
+    const int tid = threadIdx.x;
+    const int SI = (si == 1) ? 1 : 72, SX = (si == 1) ? 68 : 1;
+    auto stage = [&](double *s, int tile) {
+        for (int e = tid; e < PB_NB * 64; e += 256) {
+            int i, x;
+            if (si == 1) { i = e % PB_NB; x = e / PB_NB; } else { x = e % 64; i = e / 64; }
+            const i64 cc = (i64)tile * 64 + x, k = c1 + cc;
+            const bool ok = cc < ncols && i < nbl && k <= j0 + i + kd;
+            cp_async8_zfill(s + i * SI + x * SX, p + (j0 + (ok ? i : 0)) * si + (ok ? k : j0) * sk, ok);
+        }
+    };
+    stage(sr, tr);
+    if (tc != tr) stage(sc, tc);
+    cp_async_commit();
+    // accumulator layout of DMMA.8x8x4: lane holds C[row = lane/4][col = 2*(lane%4) + {0,1}] of each 8 x 8 tile
+    const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    const i64 rr = (i64)tr * 64 + warp * 8 + lr;  // this lane's window row
+    double acc[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    cp_async_wait<0>();
+    __syncthreads();
+    const double *scc = (tc != tr) ? sc : sr;
+    const double *ap = sr + lc * SI + (warp * 8 + lr) * SX;  // A fragment: A[row = lane/4][k = lane%4] = U12(k0 + k, row)
+    const double *bp = scc + lc * SI + lr * SX;              // B fragment: B[k = lane%4][col = lane/4] = U12(k0 + k, col)
+#pragma unroll 4
+    for (int k0 = 0; k0 < PB_NB; k0 += 4) {
+        const double av = ap[k0 * SI];
+        double bv[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) bv[t] = bp[k0 * SI + t * 8 * SX];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) pb_dmma884(acc[t][0], acc[t][1], av, bv[t]);
+    }
+    // read-modify-write of the C tile: every load before the first store
+    double cv[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const i64 cc = (i64)tc * 64 + t * 8 + 2 * lc + q;
+            cv[t][q] = (rr <= cc && cc < ncols) ? p[(c1 + rr) * si + (c1 + cc) * sk] : 0.0;
+        }
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const i64 cc = (i64)tc * 64 + t * 8 + 2 * lc + q;
+            if (rr <= cc && cc < ncols) p[(c1 + rr) * si + (c1 + cc) * sk] = cv[t][q] - acc[t][q];
+        }
+}
+
+static int pb_check(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t ldab, int &up)
+{
+    if (!h) return -1;
+    up = (uplo == 'U' || uplo == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -2;
+    if (n < 0) return -3;
+    if (kd < 0) return -4;
+    return 0;
+}
+
+extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, double *dAB, int64_t ldab, int *info)
+{
+    int up;
+    const int rc0 = pb_check(h, uplo, n, kd, ldab, up);
+    if (rc0) return rc0;
+    if (ldab < kd + 1) return -6;
+    if (!info) return -7;
+    *info = 0;
+    if (n == 0) return 0;
+    if (!dAB) return -5;
+    if (kd >= ((int64_t)1 << 24)) return -4;
+    DeviceGuard g(h->device);
+    const i64 si = up ? 1 : ldab - 1, sk = up ? ldab - 1 : 1;
+    double *p0 = dAB + (up ? kd : 0);        // 'U': the diagonal lives in band row kd
+    if (kd > n - 1) kd = n > 1 ? n - 1 : 0;  // bands beyond the matrix are never referenced (LAPACK: kn = min(kd, n-j))
+    int *d_state = h->d_info + 24;
+    const int init[2] = {0, -1};
+    BMB_CUDA(h, cudaMemcpyAsync(d_state, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    const bool blocked = kd > 64;
+    const int kdw = blocked ? PB_NB - 1 : (int)kd;
+    int ring = 16, P = 8;
+    while (ring < kdw + 1 + PB_PFD) ring <<= 1;
+    while (P < kdw + 1) P <<= 1;  // powers of two: ring addressing is an add and a mask
+    const size_t smem = (size_t)ring * P * sizeof(double);
+    typedef void (*k1_t)(i64, int, int, i64, i64, double *, int, int, int *, double *, long long *);
+    // threads >= kd+1 (one row entry each) and threads * E >= kd(kd+1)/2 (the trailing triangle)
+    k1_t k1;
+    unsigned nt1;
+    if (kdw <= 7) { k1 = pbtf2_window<32, 1>; nt1 = 32; }
+    else if (kdw <= 15) { k1 = pbtf2_window<64, 2>; nt1 = 64; }
+    else if (kdw <= 31) { k1 = pbtf2_window<128, 4>; nt1 = 128; }
+    else if (kdw <= 63) { k1 = pbtf2_window<256, 8>; nt1 = 256; }
+    else { k1 = pbtf2_window<256, 9>; nt1 = 256; }
+    BMB_CUDA(h, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long *dstats = nullptr;
+    if (h->tune.pipe_stats) {
+        if (bmb_ensure_scratch(h, 4096) != 0) return BMB200_ERR_CUDA;
+        dstats = (long long *)((char *)h->scratch + 2048);
+        BMB_CUDA(h, cudaMemsetAsync(dstats, 0, 8 * sizeof(long long), h->stream));
+    }
+    if (!blocked) {
+        k1<<<1, nt1, smem, h->stream>>>(n, (int)kd, 0, si, sk, p0, ring, P, d_state, nullptr, dstats);
+        BMB_LAUNCH_CHECK(h);
+    } else {
+        const i64 npanels = cdiv64(n, PB_NB);
+        if (bmb_ensure_scratch(h, 4096) != 0) return BMB200_ERR_CUDA;
+        double *d_rdiag = (double *)h->scratch;  // reciprocals of the panel's diagonal, K1 -> K2
+        const int ntile1d = (int)cdiv64(imin64(kd, n), 64);
+        const unsigned ntiles = (unsigned)(ntile1d * (ntile1d + 1) / 2);
+        const unsigned trsm_blocks = (unsigned)cdiv64(imin64(kd, n) * PB_TPC, 256);
+        const size_t smem3 = (size_t)2 * PB_NB * PB_SP * sizeof(double);
+        BMB_CUDA(h, cudaFuncSetAttribute(pb_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        // one graph of PB_GRAPH_PANELS panels (K1, K2, K3 each), replayed; the kernels take the panel from d_state[1]
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const i64 chunk = imin64(npanels, PB_GRAPH_PANELS);
+        // the caller's stream may be the legacy default stream, which cannot be captured: capture and replay on the handle's
+        // own stream, ordered after the caller's stream by an event (the call synchronises before it returns)
+        cudaStream_t gs = h->copy_stream;
+        BMB_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
+        BMB_CUDA(h, cudaStreamWaitEvent(gs, h->ev[3], 0));
+        BMB_CUDA(h, cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        for (i64 q = 0; q < chunk; ++q) {
+            pb_potf2_reg<<<1, 256, 0, gs>>>(n, si, sk, p0, d_state, d_rdiag);
+            pb_trsm<<<trsm_blocks, 256, 0, gs>>>(n, (int)kd, si, sk, p0, d_state, d_rdiag);
+            pb_syrk<<<ntiles, 256, smem3, gs>>>(n, (int)kd, si, sk, p0, d_state, ntile1d);
+        }
+        cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+        if (ce != cudaSuccess) { snprintf(h->err, sizeof(h->err), "dpbtrf: graph capture failed: %s", cudaGetErrorString(ce)); return BMB200_ERR_CUDA - (int)ce; }
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (ce != cudaSuccess) { cudaGraphDestroy(graph); snprintf(h->err, sizeof(h->err), "dpbtrf: graph instantiate failed: %s", cudaGetErrorString(ce)); return BMB200_ERR_CUDA - (int)ce; }
+        for (i64 q = 0; q < npanels; q += chunk) {
+            ce = cudaGraphLaunch(exec, gs);
+            if (ce != cudaSuccess) break;
+        }
+        h->launches += 3 * cdiv64(npanels, chunk) * chunk;
+        const cudaError_t se = cudaStreamSynchronize(gs);
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        BMB_CUDA(h, ce);
+        BMB_CUDA(h, se);
+    }
+    int st[2];
+    BMB_CUDA(h, cudaMemcpyAsync(st, d_state, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+    BMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (dstats) {
+        long long hs[7];
+        BMB_CUDA(h, cudaMemcpy(hs, dstats, sizeof(hs), cudaMemcpyDeviceToHost));
+        const double c = hs[4] ? (double)hs[4] : 1.0;
+        if (!blocked) fprintf(stderr, "[bmb200] pbtf2_window cycles per column (thread 0): loads + pivot %0.f | update, row store, fetch, barrier %.0f\n", hs[0] / c, hs[1] / c);
+    }
+    *info = st[0];
+    return 0;
+}
+
+extern "C" int bmb200_dpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t nrhs, const double *dAB, int64_t ldab, double *dB,
+                             int64_t ldb)
+{
+    int up;
+    const int rc0 = pb_check(h, uplo, n, kd, ldab, up);
+    if (rc0) return rc0;
+    if (nrhs < 0) return -5;
+    if (ldab < kd + 1) return -7;
+    if (ldb < (n > 1 ? n : 1)) return -9;
+    if (n == 0 || nrhs == 0) return 0;
+    if (!dAB) return -6;
+    if (!dB) return -8;
+    DeviceGuard g(h->device);
+    // DPBTRS: 'U': solve U^T y = b, then U x = y;  'L': solve L y = b, then L^T x = y  (DTBSV per right-hand side)
+    int rc;
+    if (up) {
+        rc = bmb_tbsv_t_multi(h, 1, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
+        if (rc) return rc;
+        rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, dAB, ldab, dB, ldb);
+    } else {
+        rc = bmb_cluster_solve(h, 3, n, kd, 0, nrhs, dAB, ldab, dB, ldb);
+        if (rc == 0) rc = bmb_tbsv_t_multi(h, 0, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
+    }
+    if (rc == 1) {
+        snprintf(h->err, sizeof(h->err), "dpbtrs: band width %lld is not supported by the cluster pipeline on this device", (long long)kd);
+        return BMB200_ERR_CUDA;
+    }
+    return rc;
+}

@@ -143,9 +143,10 @@ tbmv_t_cols(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 ld
 // band entries of the next column are loaded (they do not depend on x) before the current column's reduction.
 template <int KPL>  // band entries per lane: 32*KPL >= k
 __global__ void __launch_bounds__(32)
-tbsv_t_chain(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda, double *__restrict__ x, int ring)
+tbsv_t_chain(i64 n, int k, int up, int unit, const double *__restrict__ a, i64 lda, double *__restrict__ x0, i64 ldx, int ring)
 {
     extern __shared__ double xr[];  // ring of solved entries, indexed by matrix row & (ring-1)
+    double *__restrict__ x = x0 + (i64)blockIdx.x * ldx;  // one chain block per right-hand side
     const int lane = threadIdx.x, M = ring - 1;
     auto colptr = [&](i64 j) { return a + j * lda + (up ? k : 0); };  // diagonal entry of column j
     auto load_col = [&](i64 j, double (&v)[KPL]) {
@@ -313,6 +314,28 @@ static int tb_check(char uplo, char trans, char diag, int64_t n, int64_t k, int6
     return 0;
 }
 
+// tbsv 'T' for nrhs right-hand sides (columns of dB, stride ldb): one chain block each.  Also the U^T / L^T sweep of dpbtrs (pb.cu).
+int bmb_tbsv_t_multi(bmb200_ctx *h, int up, int unit, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
+{
+    if (k > 32 * 32) {
+        snprintf(h->err, sizeof(h->err), "dtbsv 'T': band width %lld > 1024 is not supported", (long long)k);
+        return BMB200_ERR_CUDA;
+    }
+    int ring = 64;
+    while (ring < k + 2) ring <<= 1;
+    const size_t smem = (size_t)ring * sizeof(double);
+#define TB_T_LAUNCH(KPL) tbsv_t_chain<KPL><<<(unsigned)nrhs, 32, smem, h->stream>>>(n, (int)k, up, unit, dA, lda, dB, ldb, ring)
+    if (k <= 32) TB_T_LAUNCH(1);
+    else if (k <= 64) TB_T_LAUNCH(2);
+    else if (k <= 128) TB_T_LAUNCH(4);
+    else if (k <= 256) TB_T_LAUNCH(8);
+    else if (k <= 512) TB_T_LAUNCH(16);
+    else TB_T_LAUNCH(32);
+#undef TB_T_LAUNCH
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
 extern "C" int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const double *dA, int64_t lda,
                             double *dx, int64_t incx)
 {
@@ -323,25 +346,7 @@ extern "C" int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag,
     if (n == 0) return 0;
     if (!dA || !dx) return -7;
     DeviceGuard g(h->device);
-    if (!(trans == 'N' || trans == 'n')) {
-        if (k > 32 * 32) {
-            snprintf(h->err, sizeof(h->err), "dtbsv 'T': band width %lld > 1024 is not supported", (long long)k);
-            return BMB200_ERR_CUDA;
-        }
-        int ring = 64;
-        while (ring < k + 2) ring <<= 1;
-        const size_t smem = (size_t)ring * sizeof(double);
-#define TB_T_LAUNCH(KPL) tbsv_t_chain<KPL><<<1, 32, smem, h->stream>>>(n, (int)k, up, unit, dA, lda, dx, ring)
-        if (k <= 32) TB_T_LAUNCH(1);
-        else if (k <= 64) TB_T_LAUNCH(2);
-        else if (k <= 128) TB_T_LAUNCH(4);
-        else if (k <= 256) TB_T_LAUNCH(8);
-        else if (k <= 512) TB_T_LAUNCH(16);
-        else TB_T_LAUNCH(32);
-#undef TB_T_LAUNCH
-        BMB_LAUNCH_CHECK(h);
-        return 0;
-    }
+    if (!(trans == 'N' || trans == 'n')) return bmb_tbsv_t_multi(h, up, unit, n, k, 1, dA, lda, dx, n > 1 ? n : 1);
     // 'U': diagonal in row k of the band array, reach k above it (mode 0 with kl = 0 divides, mode 1 does not);
     // 'L': diagonal in row 0, reach k below it (mode 2 unit, mode 3 dividing)
     const int mode = up ? (unit ? 1 : 0) : (unit ? 2 : 3);

@@ -586,6 +586,104 @@ def mul_sym_(y: torch.Tensor, uplo: str, A: BandedMatrix, x: torch.Tensor, alpha
 
 
 # ---------------------------------------------------------------------------------------------------
+# Banded Cholesky: pbtrf! / pbtrs! (src/lapack.jl:268-332), cholesky / cholesky! of Symmetric{<:BandedMatrix}
+# (banded_chol!, src/symbanded/BandedCholesky.jl:2-13) and ldiv! of the factorisation (:72-80)
+# ---------------------------------------------------------------------------------------------------
+class PosDefException(Exception):
+    """LinearAlgebra.PosDefException(info): the leading minor of order ``info`` is not positive definite."""
+
+    def __init__(self, info):
+        super().__init__(f"matrix is not positive definite; Cholesky factorization failed (leading minor of order {info}).")
+        self.info = int(info)
+
+
+def pbtrf_(uplo: str, m: int, kd: int, Adata: torch.Tensor):
+    """``pbtrf!(uplo, m, kd, A)`` (src/lapack.jl:275-291): A is the (n, rows >= kd+1) band array of the stored triangle
+    (a row-range view of ``BandedMatrix.data``), factored in place.  Returns (Adata, info)."""
+    if uplo not in ("U", "L"):  # chkuplo
+        raise ValueError(f"uplo argument must be 'U' (upper) or 'L' (lower), got {uplo}")
+    n = Adata.shape[0]
+    if n != m:
+        raise ValueError("Matrix must be square")  # lapack.jl:281
+    if Adata.shape[1] < kd + 1:
+        raise ValueError("Not enough bands")  # lapack.jl:282
+    if Adata.shape[1] > 1 and Adata.stride(1) != 1:  # chkstride1
+        raise ValueError("band rows of one column must be contiguous")
+    if n == 0:
+        return Adata, 0
+    hd = _h(Adata)
+    lda = max(1, Adata.stride(0)) if n > 1 else max(1, Adata.shape[1])
+    info = C.c_int(0)
+    rc = hd.lib.bmb200_dpbtrf(hd.h, uplo.encode(), n, kd, vp(Adata.data_ptr()), lda, C.byref(info))
+    if rc < 0 and rc > -100:
+        raise ValueError(f"invalid argument #{-rc} to LAPACK call")  # chkargsok
+    hd.check(rc, "dpbtrf")
+    return Adata, info.value
+
+
+def pbtrs_(uplo: str, m: int, kd: int, Adata: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """``pbtrs!(uplo, m, kd, A, B)`` (src/lapack.jl:305-329): B <- inv(A) B from the factor held in ``Adata``."""
+    if uplo not in ("U", "L"):
+        raise ValueError(f"uplo argument must be 'U' (upper) or 'L' (lower), got {uplo}")
+    n = Adata.shape[0]
+    if m != n or m != B.shape[0]:  # lapack.jl:311-313
+        raise DimensionMismatch(f"matrix A has dimensions ({n}, {n}), but right hand side matrix B has dimensions {tuple(B.shape)}")
+    if Adata.shape[1] < kd + 1:
+        raise ValueError("Not enough bands")
+    if n == 0:
+        return B
+    if B.dim() == 1 and _inc(B) != 1:
+        raise TypeError("right-hand side vector must be contiguous")
+    nrhs = 1 if B.dim() == 1 else B.shape[1]
+    ldb = max(1, n) if B.dim() == 1 else _ld(B)
+    hd = _h(B)
+    lda = max(1, Adata.stride(0)) if n > 1 else max(1, Adata.shape[1])
+    rc = hd.lib.bmb200_dpbtrs(hd.h, uplo.encode(), n, kd, nrhs, vp(Adata.data_ptr()), lda, vp(B.data_ptr()), ldb)
+    if rc < 0 and rc > -100:
+        raise ValueError(f"invalid argument #{-rc} to LAPACK call")
+    hd.check(rc, "dpbtrs")
+    return B
+
+
+class BandedCholesky:
+    """``Cholesky{T,<:BandedMatrix}``: ``factors`` holds U (uplo 'U': A = U'U, bandwidths (., u)) or L ('L') in the stored
+    triangle of a BandedMatrix; the other triangle is not referenced."""
+
+    def __init__(self, factors: BandedMatrix, uplo: str, info: int):
+        self.factors, self.uplo, self.info = factors, uplo, int(info)
+
+    @property
+    def shape(self):
+        return self.factors.shape
+
+    def issuccess(self) -> bool:
+        return self.info == 0
+
+    def _tri(self):
+        return _tri_data(self.uplo, self.factors)
+
+
+def cholesky_(A: BandedMatrix, uplo: str = "U", check: bool = True) -> BandedCholesky:
+    """``cholesky!(Symmetric(A, uplo))`` -> banded_chol! (BandedCholesky.jl:2-13): the `uplo` triangle of A is overwritten."""
+    d, k = _tri_data(uplo, A)
+    _, info = pbtrf_(uplo, A.m, max(k, 0), d)
+    if check and info != 0:
+        raise PosDefException(info)  # checkpositivedefinite
+    return BandedCholesky(A, uplo, info)
+
+
+def cholesky(A: BandedMatrix, uplo: str = "U", check: bool = True) -> BandedCholesky:
+    """``cholesky(Symmetric(A, uplo))`` (BandedCholesky.jl:83-89: cholcopy, then cholesky!)."""
+    return cholesky_(A.copy(), uplo, check)
+
+
+def ldiv_chol_(F: BandedCholesky, B: torch.Tensor) -> torch.Tensor:
+    """``ldiv!(F::Cholesky{T,<:BandedMatrix}, B)`` (BandedCholesky.jl:62-80) -> pbtrs!; B is overwritten."""
+    d, k = F._tri()
+    return pbtrs_(F.uplo, F.factors.m, max(k, 0), d, B)
+
+
+# ---------------------------------------------------------------------------------------------------
 # Band-aligned elementwise operations between different bandwidths (the steps either side of the hot path):
 # banded_axpy! (src/banded/BandedMatrix.jl:1006-1015, src/generic/broadcast.jl:978-1020) and copyto! (broadcast.jl:175-230)
 # ---------------------------------------------------------------------------------------------------
@@ -686,6 +784,8 @@ def factorize(A: BandedMatrix):
 
 def solve(A, b: torch.Tensor) -> torch.Tensor:
     """``A \\ b`` (linalg.jl:5-9): copies b, checks squareness, factorises, ldiv!."""
+    if isinstance(A, BandedCholesky):
+        return ldiv_chol_(A, b.clone() if b.dim() == 1 else _clone_cm(b))
     if isinstance(A, (BandedLU, TransposeFact)):
         return ldiv_(A, b.clone() if b.dim() == 1 else _clone_cm(b))
     if A.m != A.n:  # checksquare

@@ -136,6 +136,20 @@ int bmb200_dtbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n,
 int bmb200_dsbmv(bmb200_handle_t h, char uplo, int64_t n, int64_t k, double alpha, const double *dA,
                  int64_t lda, const double *dx, int64_t incx, double beta, double *dy, int64_t incy);
 
+/* ---- banded Cholesky (the factorisation half) -----------------------------------------------
+ * bmb200_dpbtrf replaces dpbtrf_ reached through pbtrf!(uplo, n, kd, AB) (src/lapack.jl:268-292), i.e. banded_chol! behind
+ * cholesky(Symmetric(::BandedMatrix)) (src/symbanded/BandedCholesky.jl:2-13).  dAB is LAPACK symmetric band storage
+ * ('U': A[i,k] at dAB[(kd+i-k) + k*ldab], i <= k; 'L': A[i,k] at dAB[(i-k) + k*ldab], i >= k), overwritten by the factor
+ * (A = U^T U or L L^T).  *info (host): 0, or j > 0 when the leading minor of order j is not positive definite (the reference
+ * turns it into PosDefException); the call synchronises.  kd <= 64 (DPBTF2: the algorithm DPBTRF runs there): bit-identical to
+ * OpenBLAS; wider bands run a blocked right-looking factorisation (DPBTRF's DSYRK/DGEMM order is unspecified): equal to
+ * rounding (tests: 1e-12 relative, ||U^T U - A|| <= 1e-14 ||A|| kd).
+ * bmb200_dpbtrs replaces dpbtrs_ reached through pbtrs!(uplo, n, kd, AB, B) (src/lapack.jl:300-332), i.e. ldiv! of the banded
+ * Cholesky factorisation (BandedCholesky.jl:72-80): dB (n x nrhs, column stride ldb) is overwritten by A^{-1} B.            */
+int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, double *dAB, int64_t ldab, int *info);
+int bmb200_dpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t nrhs, const double *dAB, int64_t ldab,
+                  double *dB, int64_t ldb);
+
 /* ---- band-aligned elementwise operations between different bandwidths ----
  * bmb200_dband_axpy replaces banded_axpy!(a, X, Y) (src/banded/BandedMatrix.jl:1006-1015 -> axpy!(a, X.data, Y.data) for equal
  * bandwidths: one FMA per slot, as OpenBLAS daxpy; src/generic/broadcast.jl:978-1020 otherwise: Y[k,j] = a*X[k,j] + Y[k,j] on

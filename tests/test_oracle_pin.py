@@ -248,3 +248,41 @@ def test_c_sbmv_matches_openblas(oracle_c, oracle_ob, rng, shape):
         if al != 0.0 and n <= 300:
             ref = al * (S @ x) + (0 if be == 0 else be * y0)
             assert np.allclose(y1, ref, rtol=1e-12, atol=1e-12)
+
+
+def _spd_band(rng, n, kd, uplo, lda_extra=0):
+    """SPD band matrix in LAPACK symmetric band storage (`uplo` triangle), diagonally dominant."""
+    ab = np.asfortranarray(rng.standard_normal((kd + 1 + lda_extra, n)))
+    ab[kd if uplo == "U" else 0, :] = 2.0 * (kd + 1) + rng.random(n)
+    return ab
+
+
+@pytest.mark.parametrize("shape", [(1, 0), (7, 2), (40, 3), (300, 16), (500, 31), (400, 33), (700, 64), (20, 40)])
+def test_c_pbtf2_pbtrs_match_openblas_bit_for_bit(oracle_c, oracle_ob, rng, shape):
+    """pbtrf! / pbtrs! (src/lapack.jl:268-332): for kd <= 64 DPBTRF runs the unblocked DPBTF2 (ILAENV: NB = 1), whose
+    operation order is defined -- the C restatement equals OpenBLAS dpbtrf_ bit for bit; dpbtrs_ = two dtbsv_ sweeps."""
+    n, kd = shape
+    for uplo, extra in itertools.product("UL", (0, 2)):
+        ab = _spd_band(rng, n, kd, uplo, extra)
+        ldab = ab.shape[0]
+        a1, a2 = ab.copy(order="F"), ab.copy(order="F")
+        assert oracle_c.pbtrf(uplo, n, kd, a1, ldab) == 0
+        assert oracle_ob.pbtrf(uplo, n, kd, a2, ldab) == 0
+        rows = slice(0, kd + 1)
+        assert np.array_equal(a1[rows], a2[rows]), (uplo, n, kd, extra)
+        b = np.asfortranarray(rng.standard_normal((n, 3)))
+        b1, b2 = b.copy(order="F"), b.copy(order="F")
+        assert oracle_c.pbtrs(uplo, n, kd, 3, a1, ldab, b1, n) == 0
+        assert oracle_ob.pbtrs(uplo, n, kd, 3, a2, ldab, b2, n) == 0
+        assert np.max(np.abs(b1 - b2)) <= 1e-13 * max(1.0, np.max(np.abs(b2))), (uplo, n, kd)
+
+
+def test_c_pbtf2_not_positive_definite(oracle_c, oracle_ob, rng):
+    n, kd = 50, 4
+    for uplo in "UL":
+        ab = _spd_band(rng, n, kd, uplo)
+        ab[kd if uplo == "U" else 0, 17] = -1.0
+        a1, a2 = ab.copy(order="F"), ab.copy(order="F")
+        assert oracle_c.pbtrf(uplo, n, kd, a1, kd + 1) == 18
+        assert oracle_ob.pbtrf(uplo, n, kd, a2, kd + 1) == 18
+        assert np.array_equal(a1, a2)

@@ -1,0 +1,10 @@
+#!/bin/bash
+# Cholesky pass: parity tests + timings + per-kernel launch list of the blocked path
+mkdir -p gpurun_out
+exec > gpurun_out/chol.log 2>&1
+set -x
+timeout 600 python -m pytest tests/test_gpu_chol.py -m gpu -x -q 2>&1 | tail -30
+timeout 200 python tools/time_chol.py 131072 1024 U 1
+timeout 200 python tools/time_chol.py 131072 1024 L 1
+timeout 200 python tools/time_chol.py 131072 256 U 1
+bash tools/gpu_chol_ncu.sh
