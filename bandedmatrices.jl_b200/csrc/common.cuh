@@ -29,6 +29,7 @@ struct bmb_tuning {
     int gbmm_ring = -1;        // 1 forces the persistent ring kernel for banded x banded, 0 disables it
     int gbmm_nt = 3;           // row tiles per work item (2 or 3)
     int gbmm_rw = 0;           // ring kernel warps per CTA (0 = by tile width)
+    int gbmm_wide = -1;        // 1 forces the K-blocked wide-band kernel (gbmm_wide.cu), 0 disables it
     int gbtrf_nopipe = 0;      // 1 disables the pipelined wide-band LU
     int gbtrf_nomw = 0;        // 1 disables the multi-warp narrow-band LU (gbtrf_mw.cu)
     int gbtrf_nostrip = 0;     // 1 disables the strip-resident interchange-free LU

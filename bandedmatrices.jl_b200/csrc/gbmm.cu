@@ -65,6 +65,9 @@ gbmm_bb_sweep(i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 
 #define GM_PAD 11         // zero pad (doubles) above and below every staged column
 #define GM_THREADS 256
 
+int bmb_gbmm_wide(bmb200_ctx *h, i64 n, i64 nu, i64 mprod, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 Cu, double alpha, const double *dA,
+                  i64 lda, const double *dB, i64 ldb, double beta, double *dC, i64 ldc);  // gbmm_wide.cu
+
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -495,8 +498,9 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
         // memory (C3: 4.45 ms), else the persistent ring kernel (one CTA per SM; C3: 4.63 ms, (64,64)x(64,64): 12.4 ms
         // where the sweep kernel took 110 ms).  tune.gbmm_ring = 1 forces the ring kernel, 0 disables it.
         const int ring_env = h->tune.gbmm_ring;
+        if (h->tune.gbmm_wide == 1 && bmb_gbmm_wide(h, n, nu, mprod, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB, ldb, beta, dC, ldc) == 0) jsplit = mprod;
         const bool tile_fits = ((size_t)(GM_TJ + Bl + Bu + 7) * PA + (size_t)GM_TJ * PB) * sizeof(double) <= 110 * 1024;
-        const bool try_ring = ring_env == 1 || (ring_env != 0 && !tile_fits);
+        const bool try_ring = jsplit == 0 && (ring_env == 1 || (ring_env != 0 && !tile_fits));
         for (int TJ = 32; TJ >= 8 && try_ring && jsplit == 0; TJ >>= 1) {  // ring kernel: widest tile whose ring fits
             const int NAr = (int)(TJ + Bl + Bu + 4 + 3);
             const int RS = 4 * ((NAr + TJ + 3) / 4);
@@ -547,6 +551,10 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
             BMB_LAUNCH_CHECK(h);
             jsplit = mprod;
         }
+        // bands too wide for staged whole columns: the K-blocked tensor-core kernel (gbmm_wide.cu)
+        if (jsplit == 0 && h->tune.gbmm_wide != 0 &&
+            bmb_gbmm_wide(h, n, nu, mprod, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB, ldb, beta, dC, ldc) == 0)
+            jsplit = mprod;
     }
     if (jsplit < m) {
         const i64 blocks = imin64(cdiv64(m - jsplit, threads / 32), (i64)h->sm_count * 8);

@@ -93,6 +93,31 @@ def test_gbmm_ring_kernel_wide_bands(bm, oracle_c, rng, shape):
         assert np.array_equal(Band(Cm.banddata_host(), n, Cl, Cu).dense(), Band(ref, n, Cl, Cu).dense())
 
 
+@pytest.mark.parametrize("shape", [(2000, 2000, 2000, 72, 70, 72, 70), (1500, 1400, 1600, 100, 90, 80, 120), (1200, 1200, 1200, 300, 300, 300, 300),
+                                   (2500, 2500, 2500, 1024, 1024, 1024, 1024), (900, 1000, 800, 200, 10, 5, 400), (300, 300, 300, 299, 299, 299, 299),
+                                   (700, 650, 720, 12, 9, 10, 14)])
+def test_gbmm_kblocked_wide_band_kernel(bm, oracle_c, rng, shape):
+    """Bands too wide for staged whole columns: the K-blocked tensor-core kernel (gbmm_wide.cu; the last shape forces it on a
+    narrow band through the tuning block).  Same per-element order => bit-identical to the per-column dgbmv_ replay."""
+    n, nu, m, Al, Au, Bl, Bu = shape
+    A, B = brand(rng, n, nu, Al, Au, corners=np.nan), brand(rng, nu, m, Bl, Bu, corners=np.nan)
+    Cl, Cu = min(n - 1, Al + Bl), min(m - 1, Au + Bu)
+    hd = bm.handle(0)
+    hd.tune("gbmm_wide", 1)
+    try:
+        for alpha, beta in [(1.0, 0.0), (-0.75, 1.25)]:
+            C0 = brand(rng, n, m, Cl, Cu)
+            ref = C0.data.copy(order="F")
+            gbmm_kernel(oracle_c, alpha, A.data, B.data, beta, ref, n, nu, m, Al, Au, Bl, Bu, Cl, Cu)
+            Cm = up(bm, C0)
+            l0 = hd.launches
+            bm.mul_(Cm, up(bm, A), up(bm, B), alpha, beta)
+            assert hd.launches > l0
+            assert np.array_equal(Band(Cm.banddata_host(), n, Cl, Cu).dense(), Band(ref, n, Cl, Cu).dense())
+    finally:
+        hd.tune("reset", 0)
+
+
 def test_gbmm_wider_C_and_banderror(bm, rng):
     """C with extra bands gets zeros/β-scaling there (test_broadcasting.jl:457-478); too few bands ⇒ BandError
     unless the missing bands are structurally zero (test_linalg.jl:272-295)."""
