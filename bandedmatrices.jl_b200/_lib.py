@@ -39,6 +39,10 @@ PROTOTYPES = {
     "bmb200_dsbmv": (C.c_int, [vp, ch, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]),
     "bmb200_dpbtrf": (C.c_int, [vp, ch, i64, i64, vp, i64, C.POINTER(C.c_int)]),
     "bmb200_dpbtrs": (C.c_int, [vp, ch, i64, i64, i64, vp, i64, vp, i64]),
+    **{f"bmb200_{p}gbmv": (C.c_int, [vp, ch, i64, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, i64]) for p in "scz"},
+    **{f"bmb200_{p}gbtrf": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(C.c_int)]) for p in "scz"},
+    **{f"bmb200_{p}gbtrs": (C.c_int, [vp, ch, i64, i64, i64, i64, vp, i64, vp, vp, i64]) for p in "scz"},
+    **{f"bmb200_{p}": (C.c_int, [vp, ch, i64, i64, vp, vp, i64, vp, i64, vp, vp, i64]) for p in ("ssbmv", "chbmv", "zhbmv")},
     "bmb200_dband_axpy": (C.c_int, [vp, i64, i64, dbl, i64, i64, vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64)]),
     "bmb200_dband_copy": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64)]),
     "bmb200_dband_lmul_block": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i64, dbl]),
@@ -58,6 +62,9 @@ PROTOTYPES = {
 INTERNAL_PROTOTYPES = {
     "bmb200_internal_divcheck": (C.c_int, [vp, i64, vp, vp, vp]),
     "bmb200_internal_divcheck2": (C.c_int, [vp, i64, vp, vp, vp]),
+    "bmb200_internal_dgbtrf_generic": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(C.c_int)]),
+    "bmb200_internal_dgbtrs_generic": (C.c_int, [vp, ch, i64, i64, i64, i64, vp, i64, vp, vp, i64]),
+    "bmb200_internal_last_gbmm_path": (C.c_int, [vp]),
     "bmb200_internal_set_tuning": (C.c_int, [vp, C.c_char_p, C.c_longlong]),
     "bmb200_internal_gbtrs_slot": (C.c_int, [vp] + [C.c_int] * 5 + [i64, i64, i64, i64, vp, i64, vp, vp, i64]),
 }
@@ -109,6 +116,10 @@ class Handle:
     def tune(self, key: str, value: int) -> None:
         """Development knob of this handle (include/bmb200_internal.h); ``tune("reset", 0)`` restores the defaults."""
         self.check(self.lib.bmb200_internal_set_tuning(self.h, key.encode(), int(value)), f"set_tuning({key})")
+
+    def last_gbmm_path(self) -> int:
+        """0 sweep, 1 tile DMMA, 2 ring DMMA, 3 K-blocked DMMA (include/bmb200_internal.h)."""
+        return int(self.lib.bmb200_internal_last_gbmm_path(self.h))
 
     def sync(self) -> None:
         self.check(self.lib.bmb200_sync(self.h), "sync")

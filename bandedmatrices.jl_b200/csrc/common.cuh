@@ -52,6 +52,7 @@ struct bmb200_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     int64_t launches = 0;
+    int last_gbmm_path = 0;    // product columns of the last bmb200_dgbmm_bb: 0 sweep, 1 tile DMMA, 2 ring DMMA, 3 K-blocked DMMA
     char err[256] = {0};
     // small persistent device scratch (LU bookkeeping, info words)
     int *d_info = nullptr;     // [0]=info, [1]=ju, spare

@@ -490,6 +490,7 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
     // The product columns go to the tensor-core kernel when the band is wide enough for dense tiles and the
     // staged tiles fit in shared memory; otherwise to the sweep kernel as well.
     i64 jsplit = 0;
+    h->last_gbmm_path = 0;
     const i64 mprod = imin64(m, nu + Bu);
     const i64 WA = Al + Au + 1, WB = Bl + Bu + 1;
     if (alpha != 0.0 && mprod > 0 && WA >= 9 && WB >= 9 && Cl == imin64(n - 1, Al + Bl) && Cu == imin64(m - 1, Au + Bu)) {
@@ -498,7 +499,10 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
         // memory (C3: 4.45 ms), else the persistent ring kernel (one CTA per SM; C3: 4.63 ms, (64,64)x(64,64): 12.4 ms
         // where the sweep kernel took 110 ms).  tune.gbmm_ring = 1 forces the ring kernel, 0 disables it.
         const int ring_env = h->tune.gbmm_ring;
-        if (h->tune.gbmm_wide == 1 && bmb_gbmm_wide(h, n, nu, mprod, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB, ldb, beta, dC, ldc) == 0) jsplit = mprod;
+        if (h->tune.gbmm_wide == 1 && bmb_gbmm_wide(h, n, nu, mprod, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB, ldb, beta, dC, ldc) == 0) {
+            jsplit = mprod;
+            h->last_gbmm_path = 3;
+        }
         const bool tile_fits = ((size_t)(GM_TJ + Bl + Bu + 7) * PA + (size_t)GM_TJ * PB) * sizeof(double) <= 110 * 1024;
         const bool try_ring = jsplit == 0 && (ring_env == 1 || (ring_env != 0 && !tile_fits));
         for (int TJ = 32; TJ >= 8 && try_ring && jsplit == 0; TJ >>= 1) {  // ring kernel: widest tile whose ring fits
@@ -526,6 +530,7 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
 #undef GR_LAUNCH
             BMB_LAUNCH_CHECK(h);
             jsplit = mprod;
+            h->last_gbmm_path = 2;
         }
         const int NA = (int)(GM_TJ + Bl + Bu + 4 + 3);
         const size_t smem = ((size_t)NA * PA + (size_t)GM_TJ * PB) * sizeof(double);
@@ -550,11 +555,14 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
 #undef GM_LAUNCH
             BMB_LAUNCH_CHECK(h);
             jsplit = mprod;
+            h->last_gbmm_path = 1;
         }
         // bands too wide for staged whole columns: the K-blocked tensor-core kernel (gbmm_wide.cu)
         if (jsplit == 0 && h->tune.gbmm_wide != 0 &&
-            bmb_gbmm_wide(h, n, nu, mprod, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB, ldb, beta, dC, ldc) == 0)
+            bmb_gbmm_wide(h, n, nu, mprod, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB, ldb, beta, dC, ldc) == 0) {
             jsplit = mprod;
+            h->last_gbmm_path = 3;
+        }
     }
     if (jsplit < m) {
         const i64 blocks = imin64(cdiv64(m - jsplit, threads / 32), (i64)h->sm_count * 8);
@@ -564,6 +572,8 @@ extern "C" int bmb200_dgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t
     }
     return 0;
 }
+
+extern "C" int bmb200_internal_last_gbmm_path(bmb200_handle_t h) { return h ? h->last_gbmm_path : -1; }
 
 // ------------------------------------------------------------------------------------------------
 // banded x dense ('N'): lane = row, NR right-hand sides per thread share every A load.

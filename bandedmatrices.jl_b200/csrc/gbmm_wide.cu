@@ -3,8 +3,8 @@
 // kernels stop at about (64,64) x (64,64); before this file such products fell back to the scalar sweep kernel).
 //
 // A CTA owns a 64 x 64 tile of C in DENSE coordinates (rows k0.., columns j0..; only tiles that meet C's band exist) and walks
-// the inner index v in blocks of KB = 16 over [max(k0-Al, j0-Bu), min(k0+63+Au, j0+63+Bl)] -- K-blocking, so shared memory
-// holds two stages of a 64 x 16 slab of A and a 16 x 64 slab of B whatever the band widths are.  In band storage a column of A
+// the inner index v in blocks of KB = 32 over [max(k0-Al, j0-Bu), min(k0+63+Au, j0+63+Bl)] -- K-blocking, so shared memory
+// holds two stages of a 64 x 32 slab of A and a 32 x 64 slab of B whatever the band widths are.  In band storage a column of A
 // is contiguous in k and a column of B is contiguous in v, so both slabs are staged with coalesced cp.async runs; entries
 // outside a band or outside the matrix are zero-filled (never read: NaN in the unused corners of the band arrays is harmless).
 // Warp w owns the eight 8 x 8 tiles of tile row w; accumulators start from beta*C (or 0), every DMMA.8x8x4 adds four terms in
@@ -12,14 +12,14 @@
 // t = alpha*B[v,j] rounded first: every C[k,j] sees the FMAs of the reference's per-column dgbmv_ sequence in the same order
 // (zero-filled terms add +0), so the result is bit-identical to the other kernels and to the oracle.  8 x 8 tiles whose own
 // v range misses a K-block skip it (warp-uniform test).
-// Shared-memory pitches: A slab sa[vv*72 + r] (72 = 8 mod 16) and B slab sb[c*20 + vv] (20 = 4 mod 16): a fragment load (4
+// Shared-memory pitches: A slab sa[vv*72 + r] (72 = 8 mod 16) and B slab sb[c*36 + vv] (36 = 4 mod 16): a fragment load (4
 // values of v x 8 rows / columns) touches every bank pair exactly twice, the minimum for 32 doubles.
 #include "common.cuh"
 
 #define GW_T 64
-#define GW_KB 16
+#define GW_KB 32
 #define GW_PA 72
-#define GW_PB 20
+#define GW_PB 36
 #define GW_THREADS 256
 
 __device__ __forceinline__ void gw_dmma884(double &d0, double &d1, double a, double b)
@@ -74,7 +74,7 @@ gbmm_bb_kblock(i64 n, i64 nu, i64 mprod, int Al, int Au, int Bl, int Bu, int Cl,
             }
             // B slab: (cc, vv) -> B[v0 + vv, j0 + cc], vv fastest
             for (int e = tid; e < GW_KB * GW_T; e += GW_THREADS) {
-                const int vv = e & (GW_KB - 1), cc = e >> 4;
+                const int vv = e & (GW_KB - 1), cc = e / GW_KB;
                 const i64 j = j0 + cc, v = v0 + vv;
                 const bool ok = v >= 0 && v < nu && j < mprod && v - j <= Bl && j - v <= Bu;
                 gw_cp8(sb(s) + cc * GW_PB + vv, b + (ok ? (Bu + v - j) + j * ldb : 0), ok);
@@ -132,6 +132,7 @@ int bmb_gbmm_wide(bmb200_ctx *h, i64 n, i64 nu, i64 mprod, i64 Al, i64 Au, i64 B
     const i64 RT = (Cl + Cu + GW_T - 1) / GW_T + 2;  // tile rows a tile column can meet
     if (ntc * RT >= ((i64)1 << 31)) return 1;
     const size_t smem = (size_t)(2 * GW_KB * GW_PA + 2 * GW_T * GW_PB) * sizeof(double);
+    BMB_CUDA(h, cudaFuncSetAttribute(gbmm_bb_kblock, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gbmm_bb_kblock<<<(unsigned)(ntc * RT), GW_THREADS, smem, h->stream>>>(n, nu, mprod, (int)Al, (int)Au, (int)Bl, (int)Bu, (int)Cl, (int)Cu, alpha,
                                                                           dA, lda, dB, ldb, beta, dC, ldc, (int)RT);
     BMB_LAUNCH_CHECK(h);

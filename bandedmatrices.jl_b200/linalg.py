@@ -684,6 +684,118 @@ def ldiv_chol_(F: BandedCholesky, B: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------------
+# The four BLAS element types: gbmv! / sbmv! / hbmv! (src/blas.jl:4-66) and LAPACK.gbtrf! / gbtrs! as the reference's lu /
+# ldiv! call them (BandedLU.jl:90-103, linalg.jl:24-63) for Float32, Float64, ComplexF32, ComplexF64.  Band arrays are the
+# package's (n, rows) tensors (one band column per tensor row), dtype float32 / float64 / complex64 / complex128.
+# ---------------------------------------------------------------------------------------------------
+_PREFIX = {torch.float32: "s", torch.float64: "d", torch.complex64: "c", torch.complex128: "z"}
+_NPTYPE = {torch.float32: np.float32, torch.float64: np.float64, torch.complex64: np.complex64, torch.complex128: np.complex128}
+
+
+def _typed(t: torch.Tensor, *others: torch.Tensor) -> str:
+    if t.dtype not in _PREFIX:
+        raise TypeError(f"element type {t.dtype} is not a BLAS float (Float32, Float64, ComplexF32, ComplexF64)")
+    for o in others:
+        if o.dtype != t.dtype:
+            raise TypeError(f"element types differ: {t.dtype} and {o.dtype}")
+    return _PREFIX[t.dtype]
+
+
+def _host_scalar(dtype: torch.dtype, v) -> np.ndarray:
+    return np.array([v], dtype=_NPTYPE[dtype])
+
+
+def _lda_of(Adata: torch.Tensor) -> int:
+    return max(1, Adata.stride(0)) if Adata.shape[0] > 1 else max(1, Adata.shape[1])
+
+
+def gbmv_(trans: str, m: int, kl: int, ku: int, alpha, Adata: torch.Tensor, x: torch.Tensor, beta, y: torch.Tensor) -> torch.Tensor:
+    """``gbmv!(trans, m, kl, ku, alpha, A, x, beta, y)`` (src/blas.jl:30-32) for the four element types; 'C' conjugates."""
+    p = _typed(Adata, x, y)
+    n = Adata.shape[0]
+    if Adata.shape[1] < kl + ku + 1:
+        raise ValueError("band data has fewer than kl+ku+1 rows")
+    lenx, leny = (n, m) if trans == "N" else (m, n)
+    if x.shape[0] != lenx or y.shape[0] != leny:
+        raise DimensionMismatch("*")
+    if m == 0 or n == 0:
+        return y
+    hd = _h(y)
+    lda = _lda_of(Adata)
+    if p == "d":
+        rc = hd.lib.bmb200_dgbmv(hd.h, trans.encode(), m, n, kl, ku, float(alpha), vp(Adata.data_ptr()), lda, vp(x.data_ptr()), _inc(x),
+                                 float(beta), vp(y.data_ptr()), _inc(y))
+    else:
+        al, be = _host_scalar(Adata.dtype, alpha), _host_scalar(Adata.dtype, beta)
+        rc = getattr(hd.lib, f"bmb200_{p}gbmv")(hd.h, trans.encode(), m, n, kl, ku, vp(al.ctypes.data), vp(Adata.data_ptr()), lda,
+                                                vp(x.data_ptr()), _inc(x), vp(be.ctypes.data), vp(y.data_ptr()), _inc(y))
+    hd.check(rc, f"{p}gbmv")
+    return y
+
+
+def hbmv_(uplo: str, k: int, alpha, Adata: torch.Tensor, x: torch.Tensor, beta, y: torch.Tensor) -> torch.Tensor:
+    """``sbmv!`` / ``hbmv!(uplo, k, alpha, A, x, beta, y)`` (src/blas.jl:36-66): the Hermitian (real types: symmetric) band
+    matvec from the stored ``uplo`` triangle; mul! of Symmetric / Hermitian{<:BandedMatrix} (symbanded.jl:72-96)."""
+    p = _typed(Adata, x, y)
+    if p == "d":
+        return sbmv_(uplo, k, alpha, Adata, x, beta, y)
+    n = Adata.shape[0]
+    if x.shape[0] != n or y.shape[0] != n:
+        raise DimensionMismatch("*")
+    if Adata.shape[1] < k + 1:
+        raise ValueError("symmetric banded data missing")
+    if n == 0:
+        return y
+    if x.data_ptr() == y.data_ptr():
+        x = x.clone()
+    hd = _h(y)
+    al, be = _host_scalar(Adata.dtype, alpha), _host_scalar(Adata.dtype, beta)
+    name = "bmb200_ssbmv" if p == "s" else f"bmb200_{p}hbmv"
+    rc = getattr(hd.lib, name)(hd.h, uplo.encode(), n, k, vp(al.ctypes.data), vp(Adata.data_ptr()), _lda_of(Adata), vp(x.data_ptr()), 1,
+                               vp(be.ctypes.data), vp(y.data_ptr()), 1)
+    hd.check(rc, name[7:])
+    return y
+
+
+def gbtrf_(m: int, kl: int, ku: int, AB: torch.Tensor):
+    """``LAPACK.gbtrf!(kl, ku, m, AB)`` (BandedLU.jl:98) for the four element types: AB is the (n, rows >= 2kl+ku+1) LU-storage
+    tensor, factored in place.  Returns (AB, d_ipiv [device int64, 1-based], info)."""
+    p = _typed(AB)
+    n = AB.shape[0]
+    mn = min(m, n)
+    d_ipiv = torch.empty(mn, dtype=torch.int64, device=AB.device)
+    if mn == 0:
+        return AB, d_ipiv, 0
+    hd = _h(AB)
+    info = C.c_int(0)
+    rc = getattr(hd.lib, f"bmb200_{p}gbtrf")(hd.h, m, n, kl, ku, vp(AB.data_ptr()), _lda_of(AB), vp(d_ipiv.data_ptr()), C.byref(info))
+    if rc < 0 and rc > -100:
+        raise ValueError(f"invalid argument #{-rc} to LAPACK call")
+    hd.check(rc, f"{p}gbtrf")
+    return AB, d_ipiv, info.value
+
+
+def gbtrs_(trans: str, kl: int, ku: int, m: int, AB: torch.Tensor, d_ipiv: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """``LAPACK.gbtrs!(trans, kl, ku, m, AB, ipiv, B)`` (linalg.jl:28,46,62) for the four element types; 'C' is the
+    conjugate-transpose solve.  B (vector or column-major matrix) is overwritten."""
+    p = _typed(AB, B)
+    n = AB.shape[0]
+    if B.shape[0] != n:
+        raise DimensionMismatch(f"B has first dimension {B.shape[0]} but needs {n}")
+    if n == 0:
+        return B
+    nrhs = 1 if B.dim() == 1 else B.shape[1]
+    ldb = max(1, n) if B.dim() == 1 else _ld(B)
+    hd = _h(B)
+    rc = getattr(hd.lib, f"bmb200_{p}gbtrs")(hd.h, trans.encode(), n, kl, ku, nrhs, vp(AB.data_ptr()), _lda_of(AB), vp(d_ipiv.data_ptr()),
+                                             vp(B.data_ptr()), ldb)
+    if rc < 0 and rc > -100:
+        raise ValueError(f"invalid argument #{-rc} to LAPACK call")
+    hd.check(rc, f"{p}gbtrs")
+    return B
+
+
+# ---------------------------------------------------------------------------------------------------
 # Band-aligned elementwise operations between different bandwidths (the steps either side of the hot path):
 # banded_axpy! (src/banded/BandedMatrix.jl:1006-1015, src/generic/broadcast.jl:978-1020) and copyto! (broadcast.jl:175-230)
 # ---------------------------------------------------------------------------------------------------

@@ -150,6 +150,41 @@ int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, double *d
 int bmb200_dpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t nrhs, const double *dAB, int64_t ldab,
                   double *dB, int64_t ldb);
 
+/* ---- Float32 / ComplexF32 / ComplexF64 instantiations ------------------------------------------
+ * src/blas.jl:4-7 generates gbmv! / sbmv! / hbmv! for the four BLAS element types; LAPACK.gbtrf! / gbtrs! (BandedLU.jl:98,
+ * linalg.jl:28,46,62 -- 'C' is a true conjugate-transpose solve) take the same four.  Same argument lists as the d-routines
+ * above with typed device pointers behind void* (complex = interleaved re,im as in Julia / Fortran); alpha and beta are passed
+ * by HOST pointer to one element of the type (the Fortran convention).  trans 'C' conjugates.  These run one generic kernel
+ * per operation (typed.cu) and agree with OpenBLAS to rounding (1e-5 / 1e-13 relative for single / double precision; pivots
+ * equal wherever a column's maximum is unique); the tuned pipelines are Float64 only.                                     */
+int bmb200_sgbmv(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, const void *alpha,
+                 const void *dA, int64_t lda, const void *dx, int64_t incx, const void *beta, void *dy, int64_t incy);
+int bmb200_sgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, void *dAB, int64_t ldab,
+                  int64_t *d_ipiv, int *info);
+int bmb200_sgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t kl, int64_t ku, int64_t nrhs, const void *dAB,
+                  int64_t ldab, const int64_t *d_ipiv, void *dB, int64_t ldb);
+int bmb200_cgbmv(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, const void *alpha,
+                 const void *dA, int64_t lda, const void *dx, int64_t incx, const void *beta, void *dy, int64_t incy);
+int bmb200_cgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, void *dAB, int64_t ldab,
+                  int64_t *d_ipiv, int *info);
+int bmb200_cgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t kl, int64_t ku, int64_t nrhs, const void *dAB,
+                  int64_t ldab, const int64_t *d_ipiv, void *dB, int64_t ldb);
+int bmb200_zgbmv(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, const void *alpha,
+                 const void *dA, int64_t lda, const void *dx, int64_t incx, const void *beta, void *dy, int64_t incy);
+int bmb200_zgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, void *dAB, int64_t ldab,
+                  int64_t *d_ipiv, int *info);
+int bmb200_zgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t kl, int64_t ku, int64_t nrhs, const void *dAB,
+                  int64_t ldab, const int64_t *d_ipiv, void *dB, int64_t ldb);
+/* symmetric (Float32) / Hermitian (complex) band matvec from one stored triangle: ssbmv_ / chbmv_ / zhbmv_ reached through
+ * sbmv! / hbmv! (src/blas.jl:36-66), i.e. mul! of Symmetric / Hermitian{<:BandedMatrix} (src/symbanded/symbanded.jl:72-96).
+ * Only the real part of the diagonal is read, as in xHBMV.  incx = incy = 1; x must not alias y.                            */
+int bmb200_ssbmv(bmb200_handle_t h, char uplo, int64_t n, int64_t k, const void *alpha, const void *dA, int64_t lda,
+                 const void *dx, int64_t incx, const void *beta, void *dy, int64_t incy);
+int bmb200_chbmv(bmb200_handle_t h, char uplo, int64_t n, int64_t k, const void *alpha, const void *dA, int64_t lda,
+                 const void *dx, int64_t incx, const void *beta, void *dy, int64_t incy);
+int bmb200_zhbmv(bmb200_handle_t h, char uplo, int64_t n, int64_t k, const void *alpha, const void *dA, int64_t lda,
+                 const void *dx, int64_t incx, const void *beta, void *dy, int64_t incy);
+
 /* ---- band-aligned elementwise operations between different bandwidths ----
  * bmb200_dband_axpy replaces banded_axpy!(a, X, Y) (src/banded/BandedMatrix.jl:1006-1015 -> axpy!(a, X.data, Y.data) for equal
  * bandwidths: one FMA per slot, as OpenBLAS daxpy; src/generic/broadcast.jl:978-1020 otherwise: Y[k,j] = a*X[k,j] + Y[k,j] on

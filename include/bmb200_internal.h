@@ -30,6 +30,18 @@ int bmb200_internal_gbtrs_slot(bmb200_handle_t h, int PF, int PB, int W, int RF,
                                int64_t kl, int64_t ku, int64_t nrhs, const double *dAB, int64_t ldab,
                                const int64_t *d_ipiv, double *dB, int64_t ldb);
 
+/* which kernel took the product columns of the last bmb200_dgbmm_bb on this handle: 0 scalar sweep (narrow bands),
+ * 1 two-CTA tile kernel (DMMA), 2 persistent ring kernel (DMMA), 3 K-blocked wide-band kernel (DMMA).  smoke() and the
+ * tests use it to assert that a wide-band product really ran on the tensor cores. */
+int bmb200_internal_last_gbmm_path(bmb200_handle_t h);
+
+/* the generic (typed.cu) LU / solve kernels instantiated for Float64: a cross-check of the tuned Float64 path, never a
+ * dispatch target of bmb200_dgbtrf / bmb200_dgbtrs. */
+int bmb200_internal_dgbtrf_generic(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, double *dAB, int64_t ldab,
+                                   int64_t *d_ipiv, int *info);
+int bmb200_internal_dgbtrs_generic(bmb200_handle_t h, char trans, int64_t n, int64_t kl, int64_t ku, int64_t nrhs,
+                                   const double *dAB, int64_t ldab, const int64_t *d_ipiv, double *dB, int64_t ldb);
+
 /* development knobs of this handle (A/B timing and diagnostics; csrc/common.cuh `bmb_tuning` lists the keys and
  * the shipped defaults; key "reset" restores them).  The library never reads the environment. */
 int bmb200_internal_set_tuning(bmb200_handle_t h, const char *key, long long value);

@@ -189,6 +189,40 @@ class _OpenBLASBackend:
                                 r(i64(ldab)), _ptr(ipiv), _ptr(b), r(i64(ldb)), r(info), C.c_long(1))
         return int(info.value)
 
+    # ---- S / C / Z instantiations (src/blas.jl:4-7; LAPACK.gbtrf! / gbtrs! for the four element types): the OpenBLAS entry points
+    # themselves, selected by the numpy dtype of the arrays.  alpha / beta go by reference as one element of the type.
+    @staticmethod
+    def prefix(dtype):
+        return {"float32": "s", "float64": "d", "complex64": "c", "complex128": "z"}[np.dtype(dtype).name]
+
+    def t_gbmv(self, trans, m, n, kl, ku, alpha, a, lda, x, beta, y):
+        p, r = self.prefix(a.dtype), C.byref
+        al, be = np.array([alpha], dtype=a.dtype), np.array([beta], dtype=a.dtype)
+        getattr(self.L, f"scipy_{p}gbmv_64_")(C.c_char_p(trans.encode()), r(i64(m)), r(i64(n)), r(i64(kl)), r(i64(ku)), _ptr(al), _ptr(a),
+                                             r(i64(lda)), _ptr(x), r(i64(1)), _ptr(be), _ptr(y), r(i64(1)), C.c_long(1))
+        return 0
+
+    def t_hbmv(self, uplo, n, k, alpha, a, lda, x, beta, y):
+        p, r = self.prefix(a.dtype), C.byref
+        name = f"scipy_{p}sbmv_64_" if p in "sd" else f"scipy_{p}hbmv_64_"
+        al, be = np.array([alpha], dtype=a.dtype), np.array([beta], dtype=a.dtype)
+        getattr(self.L, name)(C.c_char_p(uplo.encode()), r(i64(n)), r(i64(k)), _ptr(al), _ptr(a), r(i64(lda)), _ptr(x), r(i64(1)), _ptr(be),
+                              _ptr(y), r(i64(1)), C.c_long(1))
+        return 0
+
+    def t_gbtrf(self, m, n, kl, ku, ab, ldab, ipiv):
+        p, r = self.prefix(ab.dtype), C.byref
+        info = i64(0)
+        getattr(self.L, f"scipy_{p}gbtrf_64_")(r(i64(m)), r(i64(n)), r(i64(kl)), r(i64(ku)), _ptr(ab), r(i64(ldab)), _ptr(ipiv), r(info))
+        return int(info.value)
+
+    def t_gbtrs(self, trans, n, kl, ku, nrhs, ab, ldab, ipiv, b, ldb):
+        p, r = self.prefix(ab.dtype), C.byref
+        info = i64(0)
+        getattr(self.L, f"scipy_{p}gbtrs_64_")(C.c_char_p(trans.encode()), r(i64(n)), r(i64(kl)), r(i64(ku)), r(i64(nrhs)), _ptr(ab),
+                                              r(i64(ldab)), _ptr(ipiv), _ptr(b), r(i64(ldb)), r(info), C.c_long(1))
+        return int(info.value)
+
 
 _backends: dict = {}
 

@@ -112,7 +112,7 @@ def test_gbmm_kblocked_wide_band_kernel(bm, oracle_c, rng, shape):
             Cm = up(bm, C0)
             l0 = hd.launches
             bm.mul_(Cm, up(bm, A), up(bm, B), alpha, beta)
-            assert hd.launches > l0
+            assert hd.launches > l0 and hd.last_gbmm_path() == 3
             assert np.array_equal(Band(Cm.banddata_host(), n, Cl, Cu).dense(), Band(ref, n, Cl, Cu).dense())
     finally:
         hd.tune("reset", 0)

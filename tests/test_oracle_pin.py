@@ -286,3 +286,64 @@ def test_c_pbtf2_not_positive_definite(oracle_c, oracle_ob, rng):
         assert oracle_c.pbtrf(uplo, n, kd, a1, kd + 1) == 18
         assert oracle_ob.pbtrf(uplo, n, kd, a2, kd + 1) == 18
         assert np.array_equal(a1, a2)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.complex64, np.complex128])
+def test_openblas_typed_entry_points_match_dense_numpy(oracle_ob, rng, dt):
+    """The S / C / Z checker used by tests/test_gpu_typed.py (OpenBLAS {s,c,z}gbmv_ / hbmv_ / gbtrf_ / gbtrs_ entered as the
+    reference does, src/blas.jl:4-66) against a dense numpy restatement of the same operations."""
+    tol = 1e-4 if dt in (np.float32, np.complex64) else 1e-12
+    cplx = np.issubdtype(dt, np.complexfloating)
+
+    def rand(shape):
+        a = rng.standard_normal(shape)
+        return np.asfortranarray((a + 1j * rng.standard_normal(shape) if cplx else a).astype(dt))
+
+    m, n, kl, ku = 60, 50, 4, 3
+    a = rand((kl + ku + 1, n))
+    D = np.zeros((m, n), dtype=dt)
+    for j in range(n):
+        for i in range(max(0, j - ku), min(m, j + kl + 1)):
+            D[i, j] = a[ku + i - j, j]
+    alpha, beta = (0.5 - 1j, 0.25 + 0.5j) if cplx else (0.5, 0.25)
+    for trans, op in (("N", D), ("T", D.T), ("C", D.conj().T)):
+        x, y = rand(op.shape[1]), rand(op.shape[0])
+        ref = alpha * (op.astype(np.complex128 if cplx else np.float64) @ x) + beta * y
+        oracle_ob.t_gbmv(trans, m, n, kl, ku, alpha, a, kl + ku + 1, x, beta, y)
+        assert np.max(np.abs(y - ref)) <= tol * np.max(np.abs(ref))
+    # Hermitian band
+    n, k = 40, 3
+    for uplo in "UL":
+        h = rand((k + 1, n))
+        H = np.zeros((n, n), dtype=dt)
+        for j in range(n):
+            for d in range(k + 1):
+                i = j - d if uplo == "U" else j + d
+                if 0 <= i < n:
+                    v = h[k - d if uplo == "U" else d, j]
+                    if d == 0:
+                        H[j, j] = v.real
+                    else:
+                        H[i, j] = v
+                        H[j, i] = np.conj(v)
+        x, y = rand(n), rand(n)
+        ref = alpha * (H @ x) + beta * y
+        oracle_ob.t_hbmv(uplo, n, k, alpha, h, k + 1, x, beta, y)
+        assert np.max(np.abs(y - ref)) <= tol * np.max(np.abs(ref))
+    # LU + the three solves
+    n, kl, ku = 50, 3, 2
+    ldab = 2 * kl + ku + 1
+    ab = rand((ldab, n))
+    ab[:kl] = 0
+    ab[kl + ku] += 4.0
+    D = np.zeros((n, n), dtype=dt)
+    for j in range(n):
+        for i in range(max(0, j - ku), min(n, j + kl + 1)):
+            D[i, j] = ab[kl + ku + i - j, j]
+    ipiv = np.zeros(n, dtype=np.int64)
+    assert oracle_ob.t_gbtrf(n, n, kl, ku, ab, ldab, ipiv) == 0
+    for trans, op in (("N", D), ("T", D.T), ("C", D.conj().T)):
+        b = rand((n, 2))
+        ref = np.linalg.solve(op.astype(np.complex128 if cplx else np.float64), b)
+        assert oracle_ob.t_gbtrs(trans, n, kl, ku, 2, ab, ldab, ipiv, b, n) == 0
+        assert np.max(np.abs(b - ref)) <= 10 * tol * np.max(np.abs(ref))
