@@ -26,6 +26,7 @@
 #define PB_NB 64
 #define PB_PFD 8
 #define PB_GRAPH_PANELS 128
+#define PB_TRANSPOSE_KD 64  // dpbtrs: from this band width on, transpose the factor and run both sweeps as column sweeps
 #define PB_SP 72  // doubles per staged row / column of a U12 slab (pitches 68 and 72 both fit)
 
 int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
@@ -182,8 +183,8 @@ __device__ __forceinline__ void pb_sts2(unsigned addr, double x, double y) { asm
 __global__ void __launch_bounds__(256)
 pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, double *__restrict__ d_rdiag)
 {
-    __shared__ __align__(16) double xs[2][PB_NB];
-    __shared__ double rd[PB_NB];
+    __shared__ __align__(16) double xs[2][2][PB_NB];  // [buffer][x_j, x_{j+1}][column]
+    __shared__ double rd[PB_NB + 1];
     __shared__ int s_panel, s_fail;
     if (d_state[0] != 0) return;
     if (threadIdx.x == 0) { s_panel = d_state[1] + 1; d_state[1] = s_panel; s_fail = 0; }
@@ -206,7 +207,7 @@ pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restri
             const int r = 4 * a + u, c = 4 * b + w;
             v[u][w] = (upper && r <= c && c < nbl) ? p[(i64)r * si + (i64)c * sk] : ((r == c) ? 1.0 : 0.0);
         }
-    unsigned xs0 = (unsigned)__cvta_generic_to_shared(&xs[0][0]);
+    unsigned xs0 = (unsigned)__cvta_generic_to_shared(&xs[0][0][0]);
     unsigned rd0 = (unsigned)__cvta_generic_to_shared(&rd[0]);
     unsigned fl0 = (unsigned)__cvta_generic_to_shared(&s_fail);
     asm volatile("mov.u32 %0, %0;" : "+r"(xs0));
@@ -221,57 +222,96 @@ pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restri
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 #endif
 #pragma unroll 1
-    for (int jb = 0; jb < PB_NB / 4; ++jb) {
+    for (int jb = 0; jb < PB_NB / 4 && 4 * jb < nbl; ++jb) {
         const bool inwarp = warp == (jb >> 1);          // this warp holds rows 4jb..4jb+3
         const bool rowgrp = a == jb && upper;           // this thread holds a piece of them
         const int dlane = ((jb & 1) << 4) + jb;         // lane of the diagonal patch (a == b == jb)
         const bool live = upper && a >= jb;
-        const bool bgt = b > jb, bge = b >= jb;         // column 4b+w against column j = 4jb+u: > iff bgt or (b == jb and w > u)
+        const bool bgt = b > jb, bge = b >= jb;         // column 4b+w against column 4jb+u: > iff bgt or (b == jb and w > u)
         const bool isdiag = rowgrp && b == jb;
+        {   // a failure in an earlier row group stops the factorisation (one look per row group, off the per-step chain)
+            int f;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(fl0));
+            if (f) { failed = f; break; }
+        }
+        // two columns per barrier: the row-group warp takes steps j and j+1 by itself (row j+1 needs x_j only inside this warp),
+        // posts both scaled rows, and everyone else applies a rank-2 update
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 4; u += 2) {
             const int j = 4 * jb + u;
+            const unsigned buf = (unsigned)((u >> 1) & 1) * (2u * PB_NB * 8u);  // two x rows per buffer
             if (j < nbl) {  // block-uniform
-                const unsigned buf = (unsigned)(u & 1) * (PB_NB * 8u);
                 if (inwarp) {
+                    const bool two = j + 1 < nbl;
+                    double xv0[4], xv1[4];
+                    // step j
                     const double ajj = __shfl_sync(0xffffffffu, v[u][u], dlane);
-                    const bool ok = ajj > 0.0;
-                    const double rinv = pb_rsqrt(ajj);
-                    const double sc = (rowgrp && ok) ? rinv : 1.0;
-                    double xv[4];
+                    const bool ok0 = !failed && ajj > 0.0;
+                    const double rinv0 = pb_rsqrt(ajj);
+                    const double sc0 = (rowgrp && ok0) ? rinv0 : 1.0;
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
-                        const double scaled = __dmul_rn(v[u][w], sc);
+                        const double scaled = __dmul_rn(v[u][w], sc0);
                         v[u][w] = scaled;
-                        xv[w] = ((w > u) ? bge : bgt) ? scaled : 0.0;
+                        xv0[w] = (rowgrp && ok0 && ((w > u) ? bge : bgt)) ? scaled : 0.0;  // 0 in the other half-warp: its rows are not touched
                     }
-                    if (isdiag && ok) v[u][u] = __dmul_rn(ajj, rinv);
-                    if (rowgrp) { pb_sts2(xc_a + buf, xv[0], xv[1]); pb_sts2(xc_a + buf + 16u, xv[2], xv[3]); }
+                    if (isdiag && ok0) v[u][u] = __dmul_rn(ajj, rinv0);
+                    // row j+1 of the row group -= x_j[j+1] * x_j (x_j[j+1] sits in the diagonal lane)
+                    const double xj1 = __shfl_sync(0xffffffffu, xv0[u + 1], dlane);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) v[u + 1][w] = fma(-xj1, xv0[w], v[u + 1][w]);
+                    // step j+1
+                    const double ajj1 = __shfl_sync(0xffffffffu, v[u + 1][u + 1], dlane);
+                    const bool ok1 = ok0 && two && ajj1 > 0.0;
+                    const double rinv1 = pb_rsqrt(ajj1);
+                    const double sc1 = (rowgrp && ok1) ? rinv1 : 1.0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const double scaled = __dmul_rn(v[u + 1][w], sc1);
+                        v[u + 1][w] = scaled;
+                        xv1[w] = (rowgrp && ok1 && ((w > u + 1) ? bge : bgt)) ? scaled : 0.0;
+                    }
+                    if (isdiag && ok1) v[u + 1][u + 1] = __dmul_rn(ajj1, rinv1);
+                    if (rowgrp) {
+                        pb_sts2(xc_a + buf, xv0[0], xv0[1]);
+                        pb_sts2(xc_a + buf + 16u, xv0[2], xv0[3]);
+                        pb_sts2(xc_a + buf + PB_NB * 8u, xv1[0], xv1[1]);
+                        pb_sts2(xc_a + buf + PB_NB * 8u + 16u, xv1[2], xv1[3]);
+                    }
+                    if (!failed && !ok0) failed = j + 1;
+                    else if (!failed && two && !ok1) failed = j + 2;
                     if (lane == dlane) {
-                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(rd0 + 8u * j), "d"(rinv) : "memory");
-                        if (!ok) asm volatile("st.shared.u32 [%0], %1;" ::"r"(fl0), "r"(j + 1) : "memory");
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(rd0 + 8u * j), "d"(rinv0) : "memory");
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(rd0 + 8u * (j + 1)), "d"(rinv1) : "memory");
+                        if (failed) asm volatile("st.shared.u32 [%0], %1;" ::"r"(fl0), "r"(failed) : "memory");
                     }
                 }
                 __syncthreads();
-                int f;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(fl0));
-                double xr[4], xc[4];
-                pb_lds2(xr_a + buf, xr[0], xr[1]);
-                pb_lds2(xr_a + buf + 16u, xr[2], xr[3]);
-                pb_lds2(xc_a + buf, xc[0], xc[1]);
-                pb_lds2(xc_a + buf + 16u, xc[2], xc[3]);
-                if (f) { failed = f; break; }  // not positive definite: stop with the block as updated so far (DPBTF2)
                 if (live) {
-                    // rows below j of this patch: all four for a > jb; in the row group itself x[r] = 0 for r <= j makes the finished
-                    // rows a no-op, so one unpredicated rank-1 update serves both
+                    double xr0[4], xc0[4], xr1[4], xc1[4];
+                    pb_lds2(xr_a + buf, xr0[0], xr0[1]);
+                    pb_lds2(xr_a + buf + 16u, xr0[2], xr0[3]);
+                    pb_lds2(xc_a + buf, xc0[0], xc0[1]);
+                    pb_lds2(xc_a + buf + 16u, xc0[2], xc0[3]);
+                    pb_lds2(xr_a + buf + PB_NB * 8u, xr1[0], xr1[1]);
+                    pb_lds2(xr_a + buf + PB_NB * 8u + 16u, xr1[2], xr1[3]);
+                    pb_lds2(xc_a + buf + PB_NB * 8u, xc1[0], xc1[1]);
+                    pb_lds2(xc_a + buf + PB_NB * 8u + 16u, xc1[2], xc1[3]);
+                    // inside the row group x[r] = 0 for finished rows makes them a no-op; its row j+1 already has x_j's term
+                    if (a == jb) xr0[u + 1] = 0.0;
 #pragma unroll
                     for (int uu = 0; uu < 4; ++uu)
 #pragma unroll
-                        for (int w = 0; w < 4; ++w) v[uu][w] = fma(-xr[uu], xc[w], v[uu][w]);
+                        for (int w = 0; w < 4; ++w) v[uu][w] = fma(-xr1[uu], xc1[w], fma(-xr0[uu], xc0[w], v[uu][w]));
                 }
             }
         }
-        if (failed) break;
+    }
+    __syncthreads();
+    if (!failed) {
+        int f;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(fl0));
+        failed = f;
     }
 #ifdef PB_DEBUG_TIMING
     if (tid == 0 && s_panel == 10) {
@@ -554,7 +594,27 @@ extern "C" int bmb200_dpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
     DeviceGuard g(h->device);
     // DPBTRS: 'U': solve U^T y = b, then U x = y;  'L': solve L y = b, then L^T x = y  (DTBSV per right-hand side)
     int rc;
-    if (up) {
+    if (kd >= PB_TRANSPOSE_KD) {
+        // wide bands: the transposed sweep as a chain of n dot products costs ~2 us per column; instead the factor is
+        // transposed once on the device (one HBM pass, n*(kd+1) doubles of grow-only workspace) and BOTH sweeps run through the
+        // cluster pipeline as column sweeps ('N' form): same solution to rounding (the 'T' form owes 1e-13 either way).
+        const size_t need = (size_t)n * (size_t)(kd + 1) * sizeof(double);
+        if (need > h->backup_bytes) {
+            if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
+            BMB_CUDA(h, cudaMalloc(&h->backup, need));
+            h->backup_bytes = need;
+        }
+        double *tr = (double *)h->backup;
+        rc = bmb200_dband_transpose(h, n, n, up ? 0 : kd, up ? kd : 0, dAB, ldab, tr, kd + 1);
+        if (rc) return rc;
+        if (up) {
+            rc = bmb_cluster_solve(h, 3, n, kd, 0, nrhs, tr, kd + 1, dB, ldb);   // U^T = lower triangular, dividing
+            if (rc == 0) rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, dAB, ldab, dB, ldb);
+        } else {
+            rc = bmb_cluster_solve(h, 3, n, kd, 0, nrhs, dAB, ldab, dB, ldb);
+            if (rc == 0) rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, tr, kd + 1, dB, ldb);  // L^T = upper triangular, dividing
+        }
+    } else if (up) {
         rc = bmb_tbsv_t_multi(h, 1, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
         if (rc) return rc;
         rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, dAB, ldab, dB, ldb);
