@@ -360,8 +360,7 @@ pb_trsm(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
     }
     if (threadIdx.x < PB_NB) cp_async8_zfill(rdiag + threadIdx.x, d_rdiag + threadIdx.x, (int)threadIdx.x < nbl);
     cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
+    // this thread's part of its column of A12 does not depend on the staged block: the loads overlap the copies
     const int q = threadIdx.x % PB_TPC;
     const i64 c = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / PB_TPC;
     const bool live = c < ncols;  // dead lanes keep shuffling
@@ -374,6 +373,8 @@ pb_trsm(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
         const int i = s * PB_TPC + q;
         a[s] = (live && i >= i0 && i < nbl) ? p[(j0 + i) * si + k * sk] : 0.0;
     }
+    cp_async_wait<0>();
+    __syncthreads();
     const unsigned lane = threadIdx.x & 31u, base = lane & ~(unsigned)(PB_TPC - 1);
 #pragma unroll
     for (int i = 0; i < PB_NB; ++i) {
@@ -442,6 +443,15 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
     double acc[8][2];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    // the C tile does not depend on the staged slabs: its loads overlap the copies
+    double cv[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const i64 cc = (i64)tc * 64 + t * 8 + 2 * lc + q;
+            cv[t][q] = (rr <= cc && cc < ncols) ? p[(c1 + rr) * si + (c1 + cc) * sk] : 0.0;
+        }
     cp_async_wait<0>();
     __syncthreads();
     const double *scc = (tc != tr) ? sc : sr;
@@ -456,15 +466,6 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
 #pragma unroll
         for (int t = 0; t < 8; ++t) pb_dmma884(acc[t][0], acc[t][1], av, bv[t]);
     }
-    // read-modify-write of the C tile: every load before the first store
-    double cv[8][2];
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const i64 cc = (i64)tc * 64 + t * 8 + 2 * lc + q;
-            cv[t][q] = (rr <= cc && cc < ncols) ? p[(c1 + rr) * si + (c1 + cc) * sk] : 0.0;
-        }
 #pragma unroll
     for (int t = 0; t < 8; ++t)
 #pragma unroll

@@ -3,7 +3,9 @@
   C1  README workload brand(10000,10000,4,3): A*b, A*A, A\\b              (latency; bit-compared with OpenBLAS in full)
   C3  banded x banded n=2^22, (32,32)x(32,32) -> (64,64)                  (HBM roofline; column-sharded at N > 1)
   C4  banded LU + solve n=2^20, (16,16), 256 RHS                          (gbtrf: ns/column; gbtrs: HBM roofline; RHS-sharded at N > 1)
+  C3_wide  banded x banded with C5-sized bands, n=2^16, (1024,1024)^2   (FP64 tensor roofline; K-blocked DMMA kernel)
   C5  2-D Laplacian N=1024: n=2^20, l=u=1024, lu + ldiv!                  (FP64 tensor roofline; one GPU)
+      + "cholesky": the same SPD system through pbtrf! / pbtrs! (cholesky(Symmetric(A)) and its ldiv!)
 
 Every entry carries: the GPU time (CUDA events on the launching stream, best of a few repetitions after a warm-up), a
 `roofline` object (SURVEY.md 8d algorithmic bytes / flops over the measured peak), a `cpu_baseline` (the reference's own call
@@ -293,6 +295,40 @@ def run_c4(bm, L, hbm_peak, rank=0, world=1, n=1 << 20, nrhs=256):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def run_wide_gbmm(bm, L, n=1 << 16, l=1024):
+    """Banded x banded with C5-sized bands: (l,l) x (l,l) -> (2l,2l), the K-blocked tensor-core kernel (gbmm_wide.cu).  Timed at
+    n = 2^16; verified bit for bit against the per-column dgbmv_ replay on a smaller principal block (the replay costs
+    4 l^2 flops per column on one CPU core)."""
+    tpeak, tsrc = fp64_peak()
+    out = {"workload": f"BandedMatrix*BandedMatrix Float64 n=2^{int(np.log2(n))}, ({l},{l})x({l},{l})->({2*l},{2*l})"}
+    A, B = bm.brand(n, n, l, l, seed=12), bm.brand(n, n, l, l, seed=13)
+    Cm = bm.BandedMatrix.undef((n, n), (2 * l, 2 * l))
+    flops = 2.0 * (2 * l + 1) ** 2 * n
+    t, tm = _best(lambda: bm.mul_(Cm, A, B), reps=3)
+    out.update({"ms": round(t, 2), "TFLOPs": round(flops / t / 1e9, 2), "kernel_path": int(bm.handle(0).last_gbmm_path()),
+                "roofline": {"bound": "tensor", "achieved": round(flops / t / 1e9, 2), "peak": tpeak, "unit": "TFLOP/s (FP64)",
+                             "frac": round(flops / t / 1e9 / tpeak, 4), "traffic": None, "peak_source": tsrc,
+                             "kernel": "gbmm_bb_kblock (64x64 C tiles, 32-deep K-blocks, DMMA.8x8x4)"}})
+    if L is not None:
+        ns = 4 * l + 512
+        a_h, b_h = _host_band(A.data[:ns]), _host_band(B.data[:ns])
+        c_h = np.zeros((4 * l + 1, ns), order="F")
+        L.drv_set_threads(1)
+        tc = L.drv_gbmm(ns, ns, ns, l, l, l, l, 2 * l, 2 * l, 1.0, a_h.ctypes.data, a_h.shape[0], b_h.ctypes.data, b_h.shape[0], 0.0,
+                        c_h.ctypes.data, c_h.shape[0])
+        As, Bs = bm.BandedMatrix(A.data[:ns].clone(), ns, l, l), bm.BandedMatrix(B.data[:ns].clone(), ns, l, l)
+        Cs = bm.BandedMatrix.undef((ns, ns), (2 * l, 2 * l))
+        bm.mul_(Cs, As, Bs)
+        got = _host_band(Cs.data)
+        rr, jj = np.meshgrid(np.arange(got.shape[0]), np.arange(ns), indexing="ij")
+        inm = (jj + rr - 2 * l >= 0) & (jj + rr - 2 * l < ns)
+        out["parity"] = {"principal_block": ns, "entries_checked": int(inm.sum()), "bit_identical": bool(np.array_equal(got[inm], c_h[inm])),
+                         "against": "per-column OpenBLAS dgbmv_ replay of _gbmm! (gbmm.jl:306-339)"}
+        out["cpu_baseline"] = {"ms_full_extrapolated": round(1e3 * tc * n / ns, 0), "cores": 1, "kind": "reference",
+                               "sample": f"leading {ns} columns, one dgbmv_64_ per column; linear in n away from the ends"}
+    return out
+
+
 def run_c5(bm, L, hbm_peak, N=1024):
     n = N * N
     tpeak, tsrc = fp64_peak()
@@ -354,9 +390,70 @@ def run_c5(bm, L, hbm_peak, N=1024):
                              "frac": round(flops / t_f / 1e9 / tpeak, 4), "traffic": None, "peak_source": tsrc,
                              "kernel": "gbtrf_strip_kernel (strip-resident LU: diagonal-block chain + DMMA strip updates, verified diagonal pivots)"},
                 "parity": par})
-    del A, F, x, r, rhs
+    del F, x, r
+    torch.cuda.empty_cache()
+    # ---- the same system through the banded Cholesky: cholesky(Symmetric(A)) \\ b (pbtrf! / pbtrs!, BandedCholesky.jl) ----
+    try:
+        out["cholesky"] = _c5_cholesky(bm, L, A, rhs, N, tpeak, tsrc)
+    except Exception as e:  # noqa: BLE001
+        out["cholesky"] = {"error": repr(e)}
+    del A, rhs
     torch.cuda.empty_cache()
     return out
+
+
+def _c5_cholesky(bm, L, A, rhs, N, tpeak, tsrc):
+    n = A.n
+    res = {"workload": f"cholesky(Symmetric(A)) and its ldiv! on the same Laplacian: pbtrf!('U', n=2^{int(np.log2(n))}, kd={N}) + pbtrs! (1 RHS)"}
+    U = A.data[:, : N + 1].clone()  # the stored 'U' triangle (band rows 0..N), (n, N+1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _, info = bm.pbtrf_("U", n, N, U)
+    b.record()
+    b.synchronize()
+    t_f = a.elapsed_time(b)
+    x = rhs.clone()
+    bm.pbtrs_("U", n, N, U, x)  # warm-up (workspace for the transposed factor)
+    x = rhs.clone()
+    a.record()
+    bm.pbtrs_("U", n, N, U, x)
+    b.record()
+    b.synchronize()
+    t_s = a.elapsed_time(b)
+    r = rhs.clone()
+    bm.mul_(r, A, x, -1.0, 1.0)
+    flops = float(n) * (N + 1.0) ** 2
+    res.update({"info": int(info), "pbtrf_ms": round(t_f, 1), "pbtrf_TFLOPs": round(flops / t_f / 1e9, 3), "pbtrs_ms": round(t_s, 1), "flops": flops,
+                "roofline": {"bound": "tensor", "achieved": round(flops / t_f / 1e9, 3), "peak": tpeak, "unit": "TFLOP/s (FP64)",
+                             "frac": round(flops / t_f / 1e9 / tpeak, 4), "traffic": None, "peak_source": tsrc,
+                             "kernel": "pb_potf2_reg + pb_trsm + pb_syrk (DMMA) per 64-column panel, CUDA graph"},
+                "parity": {"max_residual_over_max_x_full": float(r.abs().max() / x.abs().max())}})
+    if L is not None:
+        import oracle
+
+        ob = oracle.backend("OB")
+        ns = 16 * N
+        ab = np.asfortranarray(_host_band(A.data[:ns, : N + 1]))
+        ob.set_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        iref = ob.pbtrf("U", ns, N, ab, N + 1)
+        tcf = time.perf_counter() - t0
+        xh = np.ones((ns, 1), order="F")
+        t0 = time.perf_counter()
+        ob.pbtrs("U", ns, N, 1, ab, N + 1, xh, ns)
+        tcs = time.perf_counter() - t0
+        ob.set_threads(1)
+        Us = A.data[:ns, : N + 1].clone()
+        _, i2 = bm.pbtrf_("U", ns, N, Us)
+        got = _host_band(Us)
+        rr, jj = np.meshgrid(np.arange(N + 1), np.arange(ns), indexing="ij")
+        inm = jj + rr - N >= 0
+        res["parity"].update({"sample_n": ns, "sample_info_equal": bool(iref == i2 == 0),
+                              "sample_factor_max_rel_diff": float(np.max(np.abs(got[inm] - ab[inm])) / np.max(np.abs(ab[inm]))),
+                              "tolerance": 1e-12, "against": "OpenBLAS 0.3.30 dpbtrf_64_ (blocked DPBTRF) on the leading 2^14 columns"})
+        res["cpu_baseline"] = {"pbtrf_ms_extrapolated": round(1e3 * tcf * n / ns, 0), "pbtrs_ms_extrapolated": round(1e3 * tcs * n / ns, 0),
+                               "cores": os.cpu_count(), "kind": "reference", "sample": f"leading 2^{int(np.log2(ns))} of 2^{int(np.log2(n))} columns; work per column is constant"}
+    return res
 
 
 def run_configs(bm, L, hbm_peak, rank=0, world=1, skip=()):
@@ -364,7 +461,7 @@ def run_configs(bm, L, hbm_peak, rank=0, world=1, skip=()):
     out = {}
     plan = [("C3", lambda: run_c3(bm, L, hbm_peak, rank, world)), ("C4", lambda: run_c4(bm, L, hbm_peak, rank, world))]
     if world == 1:
-        plan = [("C1", lambda: run_c1(bm, L, hbm_peak))] + plan + [("C5", lambda: run_c5(bm, L, hbm_peak))]
+        plan = [("C1", lambda: run_c1(bm, L, hbm_peak))] + plan + [("C3_wide", lambda: run_wide_gbmm(bm, L)), ("C5", lambda: run_c5(bm, L, hbm_peak))]
     for name, fn in plan:
         if name in skip:
             continue
