@@ -400,7 +400,7 @@ pb_trsm(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
 // B fragments per k-step of 4.  blockIdx.x enumerates the tiles (tr <= tc) of the largest window; tiles past the actual window
 // return.  Staged element (panel row i, window column x) sits at s[i*SI + x*SX]: the dimension that is contiguous in global
 // memory is contiguous in shared memory, and the other pitch is chosen so that a fragment load (4 values of i x 8 values of x)
-// touches every bank pair exactly twice (the minimum for 32 doubles): SX = 68 = 4 mod 16 ('U'), SI = 72 = 8 mod 16 ('L').
+// is conflict-free per half-warp (16 doubles in 16 different 8-byte banks): SX = 68 ('U'), SI = 68 ('L'), both 4 mod 16.
 __device__ __forceinline__ void pb_dmma884(double &d0, double &d1, double a, double b)
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -424,7 +424,7 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
     if ((i64)tc * 64 >= ncols) return;
     double *p = p0;
     const int tid = threadIdx.x;
-    const int SI = (si == 1) ? 1 : 72, SX = (si == 1) ? 68 : 1;
+    const int SI = (si == 1) ? 1 : 68, SX = (si == 1) ? 68 : 1;
     auto stage = [&](double *s, int tile) {
         for (int e = tid; e < PB_NB * 64; e += 256) {
             int i, x;

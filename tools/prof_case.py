@@ -54,3 +54,19 @@ elif what == "axpy":
     for _ in range(2):
         bm.axpy_(0.5, X, Y)
     torch.cuda.synchronize()
+elif what == "widegbmm":
+    l = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    A = bm.brand(n, n, l, l, seed=2)
+    B = bm.brand(n, n, l, l, seed=3)
+    C = bm.BandedMatrix.undef((n, n), (2 * l, 2 * l))
+    for _ in range(2):
+        bm.mul_(C, A, B)
+    torch.cuda.synchronize()
+elif what == "chol":
+    kd = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    d = torch.rand((n, kd + 1), dtype=torch.float64, device="cuda") - 0.5
+    d[:, kd] = 2.0 * (kd + 1)
+    for _ in range(2):
+        e = d.clone()
+        bm.pbtrf_("U", n, kd, e)
+    torch.cuda.synchronize()
