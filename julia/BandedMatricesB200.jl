@@ -191,4 +191,60 @@ function BandedMatrices._banded_broadcast!(dest::DBanded, ::typeof(identity), sr
     dest
 end
 
+# ---- banded Cholesky: shadows pbtrf! / pbtrs! (src/lapack.jl:268-332), reached from banded_chol! (src/symbanded/BandedCholesky.jl:2-13)
+# ---- and ldiv!(::Cholesky{T,<:BandedMatrix}, B) (BandedCholesky.jl:72-80), for device-resident band data ----
+function BandedMatrices.pbtrf!(uplo::Char, m::Int, kd::Int, A::DBandData)
+    LinearAlgebra.chkuplo(uplo)
+    n = size(A, 2)
+    n ≠ m && throw(ArgumentError("Matrix must be square"))
+    size(A, 1) < kd + 1 && throw(ArgumentError("Not enough bands"))
+    info = Ref{Cint}(0)
+    chk(ccall((:bmb200_dpbtrf, libbmb200), Cint, (Handle, UInt8, Int64, Int64, Ptr{Float64}, Int64, Ref{Cint}),
+              handle(), uplo, n, kd, pointer(A), max(1, stride(A, 2)), info), "dpbtrf")
+    A, BlasInt(info[])     # info > 0 -> PosDefException in cholesky! (checkpositivedefinite), exactly as today
+end
+function BandedMatrices.pbtrs!(uplo::Char, m::Int, kd::Int, A::DBandData, B::Union{DVec,DMat})
+    LinearAlgebra.chkuplo(uplo)
+    n = size(A, 2)
+    (m != n || m != size(B, 1)) && throw(DimensionMismatch("matrix A has dimensions $(size(A)), but right hand side matrix B has dimensions $(size(B))"))
+    size(A, 1) < kd + 1 && throw(ArgumentError("Not enough bands"))
+    chk(ccall((:bmb200_dpbtrs, libbmb200), Cint, (Handle, UInt8, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+              handle(), uplo, n, kd, size(B, 2), pointer(A), max(1, stride(A, 2)), pointer(B), max(1, stride(B, 2))), "dpbtrs")
+    B
+end
+
+# ---- the other three BLAS element types (src/blas.jl:4-7; LAPACK.gbtrf! / gbtrs! incl. the conjugate-transpose solve, linalg.jl:57-63):
+# ---- same argument lists, typed device pointers, alpha / beta by reference as in the Fortran interface ----
+for (p, T) in ((:s, Float32), (:c, ComplexF32), (:z, ComplexF64))
+    gbmv, gbtrf, gbtrs = Symbol(:bmb200_, p, :gbmv), Symbol(:bmb200_, p, :gbtrf), Symbol(:bmb200_, p, :gbtrs)
+    hbmv = p === :s ? :bmb200_ssbmv : Symbol(:bmb200_, p, :hbmv)
+    @eval begin
+        function BandedMatrices.gbmv!(trans::Char, m::Int, kl::Int, ku::Int, α::$T, A::B200Array{$T,2}, x::B200Array{$T,1}, β::$T, y::B200Array{$T,1})
+            chk(ccall(($(QuoteNode(gbmv)), libbmb200), Cint,
+                      (Handle, UInt8, Int64, Int64, Int64, Int64, Ref{$T}, Ptr{$T}, Int64, Ptr{$T}, Int64, Ref{$T}, Ptr{$T}, Int64),
+                      handle(), trans, m, size(A, 2), kl, ku, α, A, max(1, stride(A, 2)), x, stride(x, 1), β, y, stride(y, 1)), $(string(gbmv)))
+            y
+        end
+        function BandedMatrices.$(p === :s ? :sbmv! : :hbmv!)(uplo::Char, k::Int, α::$T, A::B200Array{$T,2}, x::B200Array{$T,1}, β::$T, y::B200Array{$T,1})
+            chk(ccall(($(QuoteNode(hbmv)), libbmb200), Cint,
+                      (Handle, UInt8, Int64, Int64, Ref{$T}, Ptr{$T}, Int64, Ptr{$T}, Int64, Ref{$T}, Ptr{$T}, Int64),
+                      handle(), uplo, size(A, 2), k, α, A, max(1, stride(A, 2)), x, 1, β, y, 1), $(string(hbmv)))
+            y
+        end
+        function LAPACK.gbtrf!(kl::Integer, ku::Integer, m::Integer, AB::B200Array{$T,2})
+            dip = B200Array{Int64,1}(undef, (min(m, size(AB, 2)),)); info = Ref{Cint}(0)
+            chk(ccall(($(QuoteNode(gbtrf)), libbmb200), Cint, (Handle, Int64, Int64, Int64, Int64, Ptr{$T}, Int64, Ptr{Int64}, Ref{Cint}),
+                      handle(), m, size(AB, 2), kl, ku, AB, stride(AB, 2), dip, info), $(string(gbtrf)))
+            LAPACK.chklapackerror(BlasInt(info[]))
+            AB, Array(dip)
+        end
+        function LAPACK.gbtrs!(trans::AbstractChar, kl::Integer, ku::Integer, m::Integer, AB::B200Array{$T,2}, ipiv::Vector{BlasInt}, B::Union{B200Array{$T,1},B200Array{$T,2}})
+            dip = B200Array(ipiv)
+            chk(ccall(($(QuoteNode(gbtrs)), libbmb200), Cint, (Handle, UInt8, Int64, Int64, Int64, Int64, Ptr{$T}, Int64, Ptr{Int64}, Ptr{$T}, Int64),
+                      handle(), trans, size(AB, 2), kl, ku, size(B, 2), AB, stride(AB, 2), dip, B, max(1, stride(B, 2))), $(string(gbtrs)))
+            B
+        end
+    end
+end
+
 end # module

@@ -1,9 +1,17 @@
 #!/bin/bash
 mkdir -p gpurun_out
 exec > gpurun_out/variants.log 2>&1
-for v in 2_2 2_3 3_2 4_2; do
-  cp gpurun_variants/lib_$v.so bandedmatrices.jl_b200/libbmb200.so
-  echo "== variant NST_MINB=$v"
-  timeout 200 python tools/time_gbmm.py 65536 1024
-  timeout 200 python tools/time_gbmm.py 262144 256
-done
+cat > /tmp/w.py <<'PY'
+import sys, torch
+sys.path.insert(0, ".")
+import bandedmatrices_b200 as bm
+hd = bm.handle(0)
+for force in (0, 1):
+    hd.tune("gbmm_wide", 1 if force else -1)
+    print("forced wide" if force else "default dispatch")
+    for n, l in ((1 << 20, 64), (1 << 21, 48), (1 << 22, 32), (1 << 20, 80), (1<<22, 16)):
+        sys.argv = ["x", str(n), str(l)]
+        exec(open("tools/time_gbmm.py").read())
+        print("   path", hd.last_gbmm_path())
+PY
+python /tmp/w.py
