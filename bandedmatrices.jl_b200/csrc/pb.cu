@@ -23,11 +23,15 @@
 //     once (cluster pipeline of gbtrs_cluster.cu for the 'N' sweep, one chain block per right-hand side for the 'T' sweep).
 #include "common.cuh"
 
-#define PB_NB 64
+#ifndef PB_NB
+#define PB_NB 64   // panel width of the blocked path (128 was measured: 719 against 557 ns/column -- the 1024-thread diagonal block spills at 64 registers)
+#endif
+#define PB_LG (PB_NB / 4)                 // lanes per row group in the register-resident diagonal block
+#define PB_K1T (PB_LG * PB_LG)           // its thread count
+#define PB_SLAB ((PB_NB + 4) * 68)       // doubles per staged U12 slab (either layout)
 #define PB_PFD 8
 #define PB_GRAPH_PANELS 128
 #define PB_TRANSPOSE_KD 64  // dpbtrs: from this band width on, transpose the factor and run both sweeps as column sweeps
-#define PB_SP 72  // doubles per staged row / column of a U12 slab (pitches 68 and 72 both fit)
 
 int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
 int bmb_tbsv_t_multi(bmb200_ctx *h, int up, int unit, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);      // tb.cu
@@ -180,12 +184,17 @@ pbtf2_window(i64 n_total, int kd_total, int blocked, i64 si, i64 sk, double *__r
 __device__ __forceinline__ void pb_lds2(unsigned addr, double &x, double &y) { asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr)); }
 __device__ __forceinline__ void pb_sts2(unsigned addr, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(x), "d"(y) : "memory"); }
 
-__global__ void __launch_bounds__(256)
-pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, double *__restrict__ d_rdiag)
+__global__ void __launch_bounds__(PB_K1T)
+pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, double *__restrict__ d_rdiag)
 {
     __shared__ __align__(16) double xs[2][2][PB_NB];  // [buffer][x_j, x_{j+1}][column]
     __shared__ double rd[PB_NB + 1];
     __shared__ int s_panel, s_fail;
+    // programmatic dependent launch (the three kernels of a panel are captured with it): this grid was launched while its
+    // predecessor was still running; nothing is read before the predecessor has completed and flushed, and the successor may
+    // be launched right away so that its launch latency hides behind this grid
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (d_state[0] != 0) return;
     if (threadIdx.x == 0) { s_panel = d_state[1] + 1; d_state[1] = s_panel; s_fail = 0; }
     __syncthreads();
@@ -197,7 +206,7 @@ pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restri
     // step, right on the dependency chain: read them once through volatile asm so that they have to stay in registers
     int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-    const int a = tid >> 4, b = tid & 15, lane = tid & 31, warp = tid >> 5;
+    const int a = tid / PB_LG, b = tid % PB_LG, lane = tid & 31, warp = tid >> 5;
     const bool upper = b >= a;
     double v[4][4];
 #pragma unroll
@@ -205,7 +214,7 @@ pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restri
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const int r = 4 * a + u, c = 4 * b + w;
-            v[u][w] = (upper && r <= c && c < nbl) ? p[(i64)r * si + (i64)c * sk] : ((r == c) ? 1.0 : 0.0);
+            v[u][w] = (upper && r <= c && c < nbl && c - r <= kd) ? p[(i64)r * si + (i64)c * sk] : ((r == c) ? 1.0 : 0.0);  // outside the band: 0, stays 0
         }
     unsigned xs0 = (unsigned)__cvta_generic_to_shared(&xs[0][0][0]);
     unsigned rd0 = (unsigned)__cvta_generic_to_shared(&rd[0]);
@@ -223,9 +232,9 @@ pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restri
 #endif
 #pragma unroll 1
     for (int jb = 0; jb < PB_NB / 4 && 4 * jb < nbl; ++jb) {
-        const bool inwarp = warp == (jb >> 1);          // this warp holds rows 4jb..4jb+3
+        const bool inwarp = warp == ((jb * PB_LG) >> 5);  // this warp holds rows 4jb..4jb+3
         const bool rowgrp = a == jb && upper;           // this thread holds a piece of them
-        const int dlane = ((jb & 1) << 4) + jb;         // lane of the diagonal patch (a == b == jb)
+        const int dlane = (jb * PB_LG + jb) & 31;        // lane of the diagonal patch (a == b == jb)
         const bool live = upper && a >= jb;
         const bool bgt = b > jb, bge = b >= jb;         // column 4b+w against column 4jb+u: > iff bgt or (b == jb and w > u)
         const bool isdiag = rowgrp && b == jb;
@@ -328,7 +337,7 @@ pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restri
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const int r = 4 * a + u, c = 4 * b + w;
-            if (upper && r <= c && c < nbl) p[(i64)r * si + (i64)c * sk] = v[u][w];
+            if (upper && r <= c && c < nbl && c - r <= kd) p[(i64)r * si + (i64)c * sk] = v[u][w];
         }
 }
 
@@ -342,8 +351,11 @@ pb_potf2_reg(i64 n_total, i64 si, i64 sk, double *__restrict__ p0, int *__restri
 __global__ void __launch_bounds__(256)
 pb_trsm(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__restrict__ d_state, const double *__restrict__ d_rdiag)
 {
-    __shared__ double u11[PB_NB * PB_NB];  // U11(i,t) at [i*NB + t] for t > i, else 0
-    __shared__ double rdiag[PB_NB];
+    extern __shared__ double pb_sm2[];
+    double *u11 = pb_sm2;                       // U11(i,t) at [i*NB + t] for t > i, else 0
+    double *rdiag = pb_sm2 + PB_NB * PB_NB;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (d_state[0] != 0) return;
     const i64 j0 = (i64)d_state[1] * PB_NB;
     if (j0 >= n) return;
@@ -400,7 +412,7 @@ pb_trsm(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
 // B fragments per k-step of 4.  blockIdx.x enumerates the tiles (tr <= tc) of the largest window; tiles past the actual window
 // return.  Staged element (panel row i, window column x) sits at s[i*SI + x*SX]: the dimension that is contiguous in global
 // memory is contiguous in shared memory, and the other pitch is chosen so that a fragment load (4 values of i x 8 values of x)
-// is conflict-free per half-warp (16 doubles in 16 different 8-byte banks): SX = 68 ('U'), SI = 68 ('L'), both 4 mod 16.
+// is conflict-free per half-warp (16 doubles in 16 different 8-byte banks): SX = NB + 4 ('U'), SI = 68 ('L'), both 4 mod 16.
 __device__ __forceinline__ void pb_dmma884(double &d0, double &d1, double a, double b)
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -409,7 +421,9 @@ __global__ void __launch_bounds__(256)
 pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__restrict__ d_state, int ntile1d)
 {
     extern __shared__ __align__(16) double pb_sm[];
-    double *sr = pb_sm, *sc = pb_sm + PB_NB * PB_SP;
+    double *sr = pb_sm, *sc = pb_sm + PB_SLAB;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (d_state[0] != 0) return;
     const i64 j0 = (i64)d_state[1] * PB_NB;
     if (j0 >= n) return;
@@ -424,7 +438,7 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
     if ((i64)tc * 64 >= ncols) return;
     double *p = p0;
     const int tid = threadIdx.x;
-    const int SI = (si == 1) ? 1 : 68, SX = (si == 1) ? 68 : 1;
+    const int SI = (si == 1) ? 1 : 68, SX = (si == 1) ? PB_NB + 4 : 1;
     auto stage = [&](double *s, int tile) {
         for (int e = tid; e < PB_NB * 64; e += 256) {
             int i, x;
@@ -504,28 +518,28 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
     const int init[2] = {0, -1};
     BMB_CUDA(h, cudaMemcpyAsync(d_state, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     const bool blocked = kd > 64;
-    const int kdw = blocked ? PB_NB - 1 : (int)kd;
-    int ring = 16, P = 8;
-    while (ring < kdw + 1 + PB_PFD) ring <<= 1;
-    while (P < kdw + 1) P <<= 1;  // powers of two: ring addressing is an add and a mask
-    const size_t smem = (size_t)ring * P * sizeof(double);
-    typedef void (*k1_t)(i64, int, int, i64, i64, double *, int, int, int *, double *, long long *);
-    // threads >= kd+1 (one row entry each) and threads * E >= kd(kd+1)/2 (the trailing triangle)
-    k1_t k1;
-    unsigned nt1;
-    if (kdw <= 7) { k1 = pbtf2_window<32, 1>; nt1 = 32; }
-    else if (kdw <= 15) { k1 = pbtf2_window<64, 2>; nt1 = 64; }
-    else if (kdw <= 31) { k1 = pbtf2_window<128, 4>; nt1 = 128; }
-    else if (kdw <= 63) { k1 = pbtf2_window<256, 8>; nt1 = 256; }
-    else { k1 = pbtf2_window<256, 9>; nt1 = 256; }
-    BMB_CUDA(h, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long *dstats = nullptr;
-    if (h->tune.pipe_stats) {
+    if (h->tune.pipe_stats && !blocked) {
         if (bmb_ensure_scratch(h, 4096) != 0) return BMB200_ERR_CUDA;
         dstats = (long long *)((char *)h->scratch + 2048);
         BMB_CUDA(h, cudaMemsetAsync(dstats, 0, 8 * sizeof(long long), h->stream));
     }
     if (!blocked) {
+        const int kdw = (int)kd;
+        int ring = 16, P = 8;
+        while (ring < kdw + 1 + PB_PFD) ring <<= 1;
+        while (P < kdw + 1) P <<= 1;  // powers of two: ring addressing is an add and a mask
+        const size_t smem = (size_t)ring * P * sizeof(double);
+        typedef void (*k1_t)(i64, int, int, i64, i64, double *, int, int, int *, double *, long long *);
+        // threads >= kd+1 (one row entry each) and threads * E >= kd(kd+1)/2 (the trailing triangle)
+        k1_t k1;
+        unsigned nt1;
+        if (kdw <= 7) { k1 = pbtf2_window<32, 1>; nt1 = 32; }
+        else if (kdw <= 15) { k1 = pbtf2_window<64, 2>; nt1 = 64; }
+        else if (kdw <= 31) { k1 = pbtf2_window<128, 4>; nt1 = 128; }
+        else if (kdw <= 63) { k1 = pbtf2_window<256, 8>; nt1 = 256; }
+        else { k1 = pbtf2_window<256, 9>; nt1 = 256; }
+        BMB_CUDA(h, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k1<<<1, nt1, smem, h->stream>>>(n, (int)kd, 0, si, sk, p0, ring, P, d_state, nullptr, dstats);
         BMB_LAUNCH_CHECK(h);
     } else {
@@ -535,7 +549,8 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
         const int ntile1d = (int)cdiv64(imin64(kd, n), 64);
         const unsigned ntiles = (unsigned)(ntile1d * (ntile1d + 1) / 2);
         const unsigned trsm_blocks = (unsigned)cdiv64(imin64(kd, n) * PB_TPC, 256);
-        const size_t smem3 = (size_t)2 * PB_NB * PB_SP * sizeof(double);
+        const size_t smem3 = (size_t)2 * PB_SLAB * sizeof(double), smem2 = (size_t)(PB_NB * PB_NB + PB_NB) * sizeof(double);
+        BMB_CUDA(h, cudaFuncSetAttribute(pb_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         BMB_CUDA(h, cudaFuncSetAttribute(pb_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         // one graph of PB_GRAPH_PANELS panels (K1, K2, K3 each), replayed; the kernels take the panel from d_state[1]
         cudaGraph_t graph = nullptr;
@@ -546,16 +561,38 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
         cudaStream_t gs = h->copy_stream;
         BMB_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
         BMB_CUDA(h, cudaStreamWaitEvent(gs, h->ev[3], 0));
-        BMB_CUDA(h, cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
-        for (i64 q = 0; q < chunk; ++q) {
-            pb_potf2_reg<<<1, 256, 0, gs>>>(n, si, sk, p0, d_state, d_rdiag);
-            pb_trsm<<<trsm_blocks, 256, 0, gs>>>(n, (int)kd, si, sk, p0, d_state, d_rdiag);
-            pb_syrk<<<ntiles, 256, smem3, gs>>>(n, (int)kd, si, sk, p0, d_state, ntile1d);
+        cudaError_t ce = cudaSuccess;
+        for (int pdl = h->tune.pb_nopdl ? 0 : 1; pdl >= 0; --pdl) {
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            auto cfg = [&](unsigned grid, unsigned block, size_t sm) {
+                cudaLaunchConfig_t c = {};
+                c.gridDim = dim3(grid);
+                c.blockDim = dim3(block);
+                c.dynamicSmemBytes = sm;
+                c.stream = gs;
+                c.attrs = attr;
+                c.numAttrs = pdl ? 1 : 0;
+                return c;
+            };
+            BMB_CUDA(h, cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+            ce = cudaSuccess;
+            for (i64 q = 0; q < chunk && ce == cudaSuccess; ++q) {
+                cudaLaunchConfig_t c1c = cfg(1, PB_K1T, 0), c2c = cfg(trsm_blocks, 256, smem2), c3c = cfg(ntiles, 256, smem3);
+                ce = cudaLaunchKernelEx(&c1c, pb_potf2_reg, (i64)n, (int)kd, si, sk, p0, d_state, d_rdiag);
+                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c2c, pb_trsm, (i64)n, (int)kd, si, sk, p0, (const int *)d_state, (const double *)d_rdiag);
+                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c3c, pb_syrk, (i64)n, (int)kd, si, sk, p0, (const int *)d_state, ntile1d);
+            }
+            const cudaError_t ee = cudaStreamEndCapture(gs, &graph);
+            if (ce == cudaSuccess) ce = ee;
+            if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (ce == cudaSuccess) break;
+            if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+            exec = nullptr;
+            (void)cudaGetLastError();
         }
-        cudaError_t ce = cudaStreamEndCapture(gs, &graph);
-        if (ce != cudaSuccess) { snprintf(h->err, sizeof(h->err), "dpbtrf: graph capture failed: %s", cudaGetErrorString(ce)); return BMB200_ERR_CUDA - (int)ce; }
-        ce = cudaGraphInstantiate(&exec, graph, 0);
-        if (ce != cudaSuccess) { cudaGraphDestroy(graph); snprintf(h->err, sizeof(h->err), "dpbtrf: graph instantiate failed: %s", cudaGetErrorString(ce)); return BMB200_ERR_CUDA - (int)ce; }
+        if (ce != cudaSuccess) { snprintf(h->err, sizeof(h->err), "dpbtrf: graph capture / instantiation failed: %s", cudaGetErrorString(ce)); return BMB200_ERR_CUDA - (int)ce; }
         for (i64 q = 0; q < npanels; q += chunk) {
             ce = cudaGraphLaunch(exec, gs);
             if (ce != cudaSuccess) break;
