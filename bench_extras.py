@@ -140,6 +140,24 @@ def run_secondary(bm):
     out["EW"] = {"n": ne, "axpy_equal_bands_ms": round(t_eq, 3), "axpy_equal_GBs": round(3 * 8.0 * 8 * ne / t_eq / 1e6, 1),
                  "axpy_(4,3)_into_(5,4)_ms": round(t_ne, 3), "note": "unequal bandwidths also run the BandError counting pass over X and synchronise"}
     del Xe, Ye, Yw
+    # ---- gbmv on the wide band (the C5 residual b - A x: every gbmv with l+u+1 > 16 takes the sweep kernel) ----
+    xw, yw = torch.rand(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+    t_gw = _time(lambda: bm.mul_(yw, A, xw, 1.0, 0.0), reps=3)
+    by_gw = 8.0 * n * (2 * N + 1) + 16.0 * n
+    out["GBMV_wide"] = {"n": n, "l": N, "u": N, "ms": round(t_gw, 3), "GBs": round(by_gw / t_gw / 1e6, 1), "algorithmic_bytes": by_gw}
+    del xw, yw
+    # ---- the other element types: gbmv 'N' and 'C' on the C2 band shape (4,3), n = 2^26 ----
+    nt = 1 << 26
+    ty = {}
+    for name, dt, eb in (("Float32", torch.float32, 4), ("ComplexF32", torch.complex64, 8), ("ComplexF64", torch.complex128, 16)):
+        Ad = torch.randn((nt, 8), dtype=dt, device="cuda")
+        xt, yt = torch.randn(nt, dtype=dt, device="cuda"), torch.empty(nt, dtype=dt, device="cuda")
+        tn = _time(lambda: bm.gbmv_("N", nt, 4, 3, 1.0, Ad, xt, 0.0, yt), reps=3)
+        tc = _time(lambda: bm.gbmv_("C", nt, 4, 3, 1.0, Ad, xt, 0.0, yt), reps=3)
+        byt = float(eb) * nt * 10
+        ty[name] = {"gbmv_N_ms": round(tn, 3), "gbmv_N_GBs": round(byt / tn / 1e6, 1), "gbmv_C_ms": round(tc, 3), "gbmv_C_GBs": round(byt / tc / 1e6, 1)}
+        del Ad, xt, yt
+    out["TYPED"] = {"n": nt, "bands": [4, 3], "algorithmic_bytes_per_element_size": 10 * nt, **ty}
     out["TB"] = {"n": n, "k": N, "tbsv_U_ms": round(t_sv, 2), "tbmv_U_ms": round(t_mv, 3), "tbmv_GBs": round(by / t_mv / 1e6, 1),
                  "algorithmic_bytes": by}
     return out
