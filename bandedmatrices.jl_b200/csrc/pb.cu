@@ -489,6 +489,40 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
         }
 }
 
+// ---- helpers of the narrow-band dpbtrs: both sweeps run through the tuned multi-RHS back substitution of bmb200_dgbtrs ----
+// A lower-triangular solve becomes an upper-triangular one under the reversal i -> n-1-i.  `mode` 0: dst = reversal of U^T
+// ('U' factor, first sweep), 1: dst = reversal of L ('L' factor, first sweep); dst is 'U' triangular-band storage, ld = kd+1.
+__global__ void __launch_bounds__(256)
+pb_reverse_factor(int mode, i64 n, int kd, const double *__restrict__ src, i64 lds, double *__restrict__ dst)
+{
+    const i64 total = n * (kd + 1);
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 jp = e / (kd + 1);
+        const int b = (int)(e - jp * (kd + 1));
+        double v = 0.0;
+        if (jp - (kd - b) >= 0) {  // in-matrix entry M[i', j'] with i' = j' - (kd - b)
+            if (mode == 0) v = src[b + (n - 1 - jp + (kd - b)) * lds];   // U[n-1-j', n-1-i'] : band row b of column n-1-i'
+            else v = src[(kd - b) + (n - 1 - jp) * lds];                 // L[n-1-i', n-1-j'] : band row kd-b of column n-1-j'
+        }
+        dst[e] = v;
+    }
+}
+__global__ void pb_iota(i64 n, i64 *__restrict__ p)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = i + 1;
+}
+__global__ void pb_reverse_rows(i64 n, i64 nrhs, double *__restrict__ b, i64 ldb)
+{
+    const i64 half = n / 2, total = half * nrhs;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 q = e / half, i = e - q * half;
+        double *c = b + q * ldb;
+        const double t = c[i];
+        c[i] = c[n - 1 - i];
+        c[n - 1 - i] = t;
+    }
+}
+
 static int pb_check(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t ldab, int &up)
 {
     if (!h) return -1;
@@ -652,13 +686,38 @@ extern "C" int bmb200_dpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
             rc = bmb_cluster_solve(h, 3, n, kd, 0, nrhs, dAB, ldab, dB, ldb);
             if (rc == 0) rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, tr, kd + 1, dB, ldb);  // L^T = upper triangular, dividing
         }
-    } else if (up) {
-        rc = bmb_tbsv_t_multi(h, 1, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
-        if (rc) return rc;
-        rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, dAB, ldab, dB, ldb);
     } else {
-        rc = bmb_cluster_solve(h, 3, n, kd, 0, nrhs, dAB, ldab, dB, ldb);
-        if (rc == 0) rc = bmb_tbsv_t_multi(h, 0, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
+        // narrow bands: both sweeps through bmb200_dgbtrs('N') with kl = 0 and identity pivots, i.e. its multi-RHS back
+        // substitution (slot-scheduled / register-window kernels: ~45 ns per column for all right-hand sides together, where
+        // the single-warp chain of the transposed dtbsv took ~250).  The lower-triangular sweep is the upper-triangular one of
+        // the REVERSED system (i -> n-1-i): the factor is gathered once into reversed 'U' storage, the right-hand sides are
+        // reversed in place before and after.  Column-oriented ('N'-form) sweeps on both sides: equal to DPBTRS to rounding.
+        const size_t fbytes = (size_t)n * (size_t)(kd + 1) * sizeof(double), need = fbytes + (size_t)n * sizeof(i64);
+        if (need > h->backup_bytes) {
+            if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
+            BMB_CUDA(h, cudaMalloc(&h->backup, need));
+            h->backup_bytes = need;
+        }
+        double *M = (double *)h->backup;
+        i64 *idp = (i64 *)((char *)h->backup + fbytes);
+        const unsigned gb = (unsigned)imin64(cdiv64(n * (kd + 1), 256), (i64)h->sm_count * 16);
+        const unsigned gr = (unsigned)imin64(cdiv64(imax64(1, (n / 2) * nrhs), 256), (i64)h->sm_count * 16);
+        pb_iota<<<(unsigned)imin64(cdiv64(n, 256), (i64)h->sm_count * 8), 256, 0, h->stream>>>(n, idp);
+        pb_reverse_factor<<<gb, 256, 0, h->stream>>>(up ? 0 : 1, n, (int)kd, dAB, ldab, M);
+        pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
+        h->launches += 3;
+        BMB_CUDA(h, cudaGetLastError());
+        rc = bmb200_dgbtrs(h, 'N', n, 0, kd, nrhs, M, kd + 1, idp, dB, ldb);            // U^T y = b  /  L y = b, reversed
+        if (rc) return rc;
+        pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
+        BMB_LAUNCH_CHECK(h);
+        if (up) {
+            rc = bmb200_dgbtrs(h, 'N', n, 0, kd, nrhs, dAB, ldab, idp, dB, ldb);          // U x = y
+        } else {
+            rc = bmb200_dband_transpose(h, n, n, kd, 0, dAB, ldab, M, kd + 1);            // L^T in 'U' storage
+            if (rc == 0) rc = bmb200_dgbtrs(h, 'N', n, 0, kd, nrhs, M, kd + 1, idp, dB, ldb);  // L^T x = y
+        }
+        return rc;
     }
     if (rc == 1) {
         snprintf(h->err, sizeof(h->err), "dpbtrs: band width %lld is not supported by the cluster pipeline on this device", (long long)kd);
