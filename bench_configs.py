@@ -3,6 +3,7 @@
   C1  README workload brand(10000,10000,4,3): A*b, A*A, A\\b              (latency; bit-compared with OpenBLAS in full)
   C3  banded x banded n=2^22, (32,32)x(32,32) -> (64,64)                  (HBM roofline; column-sharded at N > 1)
   C4  banded LU + solve n=2^20, (16,16), 256 RHS                          (gbtrf: ns/column; gbtrs: HBM roofline; RHS-sharded at N > 1)
+  C4_chol  the C4 shape through the banded Cholesky: pbtrf! + pbtrs!, 256 RHS (factor bit-compared with OpenBLAS in full)
   C3_wide  banded x banded with C5-sized bands, n=2^16, (1024,1024)^2   (FP64 tensor roofline; K-blocked DMMA kernel)
   C5  2-D Laplacian N=1024: n=2^20, l=u=1024, lu + ldiv!                  (FP64 tensor roofline; one GPU)
       + "cholesky": the same SPD system through pbtrf! / pbtrs! (cholesky(Symmetric(A)) and its ldiv!)
@@ -294,6 +295,51 @@ def run_c4(bm, L, hbm_peak, rank=0, world=1, n=1 << 20, nrhs=256):
     return out
 
 
+def run_c4_cholesky(bm, L, n=1 << 20, kd=16, nrhs=256):
+    """The C4 shape through the banded Cholesky: pbtrf!('U', n=2^20, kd=16) + pbtrs! with 256 right-hand sides, on an SPD band
+    (random band + dominant diagonal).  kd <= 64 is the DPBTF2 regime: the factor is compared BIT FOR BIT with OpenBLAS
+    dpbtrf_64_ at the full size."""
+    out = {"workload": f"banded Cholesky + solve Float64 n=2^{int(np.log2(n))}, kd={kd}, {nrhs} RHS (pbtrf! then pbtrs!, uplo 'U')"}
+    g = torch.Generator(device="cuda").manual_seed(99)
+    U0 = torch.rand((n, kd + 1), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    U0[:, kd] = 2.0 * (kd + 1) + torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    U = U0.clone()
+    keep = {}
+
+    def factor():
+        keep["info"] = bm.pbtrf_("U", n, kd, U)[1]
+
+    t_f, _ = _best(factor, reps=2, setup=lambda: U.copy_(U0))
+    Bfull = torch.rand((nrhs, n), dtype=torch.float64, device="cuda", generator=g)
+    X = bm.colmajor(n, nrhs)
+    t_s, _ = _best(lambda: bm.pbtrs_("U", n, kd, U, X), reps=3, setup=lambda: X.copy_(Bfull.T))
+    out.update({"info": int(keep["info"]), "pbtrf_ms": round(t_f, 2), "pbtrf_ns_per_column": round(1e6 * t_f / n, 1), "pbtrs_ms": round(t_s, 2),
+                "note": "both are chains of n dependent steps (sqrt + divide per column; a sweep per right-hand side): latency-bound, no roofline claim"})
+    if L is not None:
+        import oracle
+
+        ob = oracle.backend("OB")
+        ab = np.asfortranarray(_host_band(U0))
+        ob.set_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        iref = ob.pbtrf("U", n, kd, ab, kd + 1)
+        tcf = time.perf_counter() - t0
+        nchk = 16
+        bh = np.asfortranarray(Bfull[:nchk].T.cpu().numpy())
+        t0 = time.perf_counter()
+        ob.pbtrs("U", n, kd, nchk, ab, kd + 1, bh, n)
+        tcs = time.perf_counter() - t0
+        ob.set_threads(1)
+        got = X[:, :nchk].cpu().numpy()
+        out["parity"] = {"info_equal": bool(iref == keep["info"] == 0), "factor_bit_identical": _bits_equal(_host_band(U), ab),
+                         f"solution_max_rel_diff_{nchk}rhs": float(np.max(np.abs(got - bh)) / np.max(np.abs(bh))), "solution_tolerance": 1e-13,
+                         "against": "OpenBLAS 0.3.30 dpbtrf_64_ (= DPBTF2 for kd <= 64) / dpbtrs_64_ at the full n"}
+        out["cpu_baseline"] = {"pbtrf_ms": round(1e3 * tcf, 1), "pbtrf_ns_per_column": round(1e9 * tcf / n, 1),
+                               "pbtrs_ms_extrapolated": round(1e3 * tcs * nrhs / nchk, 1), "cores": os.cpu_count(), "kind": "reference",
+                               "sample": f"dpbtrf_64_ on the full matrix; dpbtrs_64_ on {nchk} of {nrhs} right-hand sides, linear in nrhs"}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def run_wide_gbmm(bm, L, n=1 << 16, l=1024):
     """Banded x banded with C5-sized bands: (l,l) x (l,l) -> (2l,2l), the K-blocked tensor-core kernel (gbmm_wide.cu).  Timed at
@@ -461,7 +507,8 @@ def run_configs(bm, L, hbm_peak, rank=0, world=1, skip=()):
     out = {}
     plan = [("C3", lambda: run_c3(bm, L, hbm_peak, rank, world)), ("C4", lambda: run_c4(bm, L, hbm_peak, rank, world))]
     if world == 1:
-        plan = [("C1", lambda: run_c1(bm, L, hbm_peak))] + plan + [("C3_wide", lambda: run_wide_gbmm(bm, L)), ("C5", lambda: run_c5(bm, L, hbm_peak))]
+        plan = [("C1", lambda: run_c1(bm, L, hbm_peak))] + plan + [("C4_chol", lambda: run_c4_cholesky(bm, L)), ("C3_wide", lambda: run_wide_gbmm(bm, L)),
+                                                                   ("C5", lambda: run_c5(bm, L, hbm_peak))]
     for name, fn in plan:
         if name in skip:
             continue
