@@ -14,7 +14,7 @@ repository root loads this directory under that name).
 from ._lib import BMB200Error, Handle, LIB_PATH, PROTOTYPES, handle, load
 from .banded import (BandedMatrix, BandError, DimensionMismatch, LAPACKException, Transposed, bandeddata, bandwidth,
                      bandwidths, brand, colmajor, to_colmajor)
-from .linalg import (gbmv_, hbmv_, gbtrf_, gbtrs_, BandedCholesky, PosDefException, cholesky, cholesky_, ldiv_chol_, pbtrf_, pbtrs_, BandedLU, TransposeFact, axpby_, axpy_, badd, bscale, bsub, copyto_, similar, factorize, gbmm_, gbmv_host, ldiv_, ldiv_tri_, lmul_tri_, lu, lu_, matmul, mul_,
+from .linalg import (gbmv_, hbmv_, gbtrf_, gbtrs_, gbmm_typed_, gbmm_bd_typed_, BandedCholesky, PosDefException, cholesky, cholesky_, ldiv_chol_, pbtrf_, pbtrs_, BandedLU, TransposeFact, axpby_, axpy_, badd, bscale, bsub, copyto_, similar, factorize, gbmm_, gbmv_host, ldiv_, ldiv_tri_, lmul_tri_, lu, lu_, matmul, mul_,
                      mul_sym_, sbmv_, solve, tbmv_, tbsv_)
 
 __all__ = [
@@ -22,5 +22,5 @@ __all__ = [
     "BMB200Error", "Handle", "handle", "load", "LIB_PATH", "PROTOTYPES", "bandeddata", "bandwidth", "bandwidths",
     "brand", "colmajor", "to_colmajor", "mul_", "matmul", "gbmm_", "lu", "lu_", "ldiv_", "solve", "factorize",
     "gbmv_host", "tbsv_", "tbmv_", "ldiv_tri_", "lmul_tri_", "sbmv_", "mul_sym_", "axpy_", "copyto_", "axpby_", "badd", "bsub",
-    "bscale", "similar", "gbmv_", "hbmv_", "gbtrf_", "gbtrs_", "BandedCholesky", "PosDefException", "cholesky", "cholesky_", "ldiv_chol_", "pbtrf_", "pbtrs_",
+    "bscale", "similar", "gbmv_", "hbmv_", "gbtrf_", "gbtrs_", "gbmm_typed_", "gbmm_bd_typed_", "BandedCholesky", "PosDefException", "cholesky", "cholesky_", "ldiv_chol_", "pbtrf_", "pbtrs_",
 ]

@@ -43,6 +43,12 @@ PROTOTYPES = {
     **{f"bmb200_{p}gbtrf": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, C.POINTER(C.c_int)]) for p in "scz"},
     **{f"bmb200_{p}gbtrs": (C.c_int, [vp, ch, i64, i64, i64, i64, vp, i64, vp, vp, i64]) for p in "scz"},
     **{f"bmb200_{p}": (C.c_int, [vp, ch, i64, i64, vp, vp, i64, vp, i64, vp, vp, i64]) for p in ("ssbmv", "chbmv", "zhbmv")},
+    **{f"bmb200_{p}tbsv": (C.c_int, [vp, ch, ch, ch, i64, i64, vp, i64, vp, i64]) for p in "scz"},
+    **{f"bmb200_{p}tbmv": (C.c_int, [vp, ch, ch, ch, i64, i64, vp, i64, vp, i64]) for p in "scz"},
+    **{f"bmb200_{p}pbtrf": (C.c_int, [vp, ch, i64, i64, vp, i64, C.POINTER(C.c_int)]) for p in "scz"},
+    **{f"bmb200_{p}pbtrs": (C.c_int, [vp, ch, i64, i64, i64, vp, i64, vp, i64]) for p in "scz"},
+    **{f"bmb200_{p}gbmm_bb": (C.c_int, [vp] + [i64] * 9 + [vp, vp, i64, vp, i64, vp, vp, i64]) for p in "scz"},
+    **{f"bmb200_{p}gbmm_bd": (C.c_int, [vp, ch, i64, i64, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, i64]) for p in "scz"},
     "bmb200_dband_axpy": (C.c_int, [vp, i64, i64, dbl, i64, i64, vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64)]),
     "bmb200_dband_copy": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64)]),
     "bmb200_dband_lmul_block": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i64, dbl]),

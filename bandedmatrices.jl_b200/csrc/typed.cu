@@ -8,8 +8,10 @@
 //   thbmv        Hermitian (real types: symmetric) band matvec from one stored triangle, one thread per row
 //   tgbtf2       unblocked partial-pivot band LU in LAPACK's xGBTF2 order (pivot = first maximum of |re|+|im|, multipliers scaled
 //                by the reciprocal of the pivot, rank-1 update), one CTA, three barriers per column
-//   tgbtrs       solve with the factors for op in {N, T, C}, one CTA per right-hand side, the right-hand side streamed through a
-//                shared-memory window
+//   tgbtrs       solve with the factors for op in {N, T, C}, one CTA per right-hand side
+//   ttbmv/ttbsv  triangular band multiply / solve for op in {N, T, C} (tbmv! / tbsv!, src/blas.jl:71-141)
+//   tpbtf2       Hermitian band Cholesky in xPBTF2's order, one CTA; pbtrs = two ttbsv sweeps (pbtrf! / pbtrs!, src/lapack.jl:268-332)
+//   tgbmm_bb/bd  banded x banded and banded x dense, one thread per entry of C, inner index ascending (gbmm!, src/banded/gbmm.jl)
 // OpenBLAS' operation order is unspecified for these types (SIMD dot / complex kernels): parity is to rounding (tests: 1e-5 /
 // 1e-13 relative for single / double precision), pivots compared exactly on well-separated columns.
 #include <cuComplex.h>
@@ -342,6 +344,178 @@ tgbtrs(int op, i64 n, i64 kl, i64 ku, const T *__restrict__ ab, i64 ldab, const 
     }
 }
 
+// ---- tbmv: x <- op(T) x, T triangular band ('U': T[i,j] at a[(k+i-j) + j*lda], 'L': a[(i-j) + j*lda]); op = 0 'N', 1 'T', 2 'C' ----
+// one thread per row of op(T); the result goes to `y` (scratch) and is copied back by the caller
+template <typename T>
+__global__ void __launch_bounds__(256)
+ttbmv(int up, int op, int unit, i64 n, i64 k, const T *__restrict__ a, i64 lda, const T *__restrict__ x, T *__restrict__ y)
+{
+    typedef Num<T> N;
+    const bool cj = op == 2;
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const T dg = a[(up ? k : 0) + i * lda];
+        T acc = unit ? x[i] : N::mul(cj ? N::conj(dg) : dg, x[i]);
+        if (op == 0) {
+            if (up) { const i64 j1 = i + k < n - 1 ? i + k : n - 1; for (i64 j = i + 1; j <= j1; ++j) acc = N::fma(a[(k + i - j) + j * lda], x[j], acc); }
+            else { const i64 j0 = i - k > 0 ? i - k : 0; for (i64 j = i - 1; j >= j0; --j) acc = N::fma(a[(i - j) + j * lda], x[j], acc); }
+        } else {  // row i of op(T) = column i of T, contiguous
+            const T *col = a + i * lda + (up ? k : 0);
+            if (up) { const i64 dmax = i < k ? i : k; for (i64 d = 1; d <= dmax; ++d) acc = N::fma(cj ? N::conj(col[-d]) : col[-d], x[i - d], acc); }
+            else { const i64 dmax = n - 1 - i < k ? n - 1 - i : k; for (i64 d = 1; d <= dmax; ++d) acc = N::fma(cj ? N::conj(col[d]) : col[d], x[i + d], acc); }
+        }
+        y[i] = acc;
+    }
+}
+
+// ---- tbsv: x <- op(T)^{-1} x; one CTA per right-hand side (column of b0, stride ldb); correctness-first chain ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+ttbsv(int up, int op, int unit, i64 n, i64 k, const T *__restrict__ a, i64 lda, T *__restrict__ b0, i64 ldb)
+{
+    typedef Num<T> N;
+    T *x = b0 + (i64)blockIdx.x * ldb;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const bool cj = op == 2;
+    __shared__ T s_x;
+    __shared__ T s_red[8];
+    const bool ascending = (op == 0) ? !up : up;  // order in which the unknowns become known
+    for (i64 c = 0; c < n; ++c) {
+        const i64 j = ascending ? c : n - 1 - c;
+        const T *col = a + j * lda + (up ? k : 0);  // diagonal entry of column j; T[j-d, j] = col[-d] ('U'), T[j+d, j] = col[+d] ('L')
+        if (op == 0) {
+            // column sweep: x[j] /= T[j,j]; the entries in reach get -x[j] * T[., j]
+            if (tid == 0) { const T xj = unit ? x[j] : N::mul(x[j], N::recip(col[0])); x[j] = xj; s_x = xj; }
+            __syncthreads();
+            const T xj = s_x;
+            const i64 reach = up ? (k < j ? k : j) : (k < n - 1 - j ? k : n - 1 - j);
+            for (i64 d = 1 + tid; d <= reach; d += nt) {
+                const i64 i = up ? j - d : j + d;
+                x[i] = N::fma(N::neg(xj), up ? col[-d] : col[d], x[i]);
+            }
+            __syncthreads();
+        } else {
+            // dot-product sweep: x[j] = (x[j] - sum_d op(T[j-+d, j]) x[j-+d]) / op(T[j,j])
+            const i64 reach = up ? (k < j ? k : j) : (k < n - 1 - j ? k : n - 1 - j);
+            T acc = N::zero();
+            for (i64 d = 1 + tid; d <= reach; d += nt) {
+                const T t = up ? col[-d] : col[d];
+                acc = N::fma(cj ? N::conj(t) : t, x[up ? j - d : j + d], acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = N::add(acc, N::shfl_xor(acc, o));
+            if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                T sum = s_red[0];
+                for (int w = 1; w < (nt >> 5); ++w) sum = N::add(sum, s_red[w]);
+                T v = N::add(x[j], N::neg(sum));
+                if (!unit) v = N::mul(v, N::recip(cj ? N::conj(col[0]) : col[0]));
+                x[j] = v;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- pbtf2: unblocked Hermitian band Cholesky in xPBTF2's order; one CTA; up: A = U^H U, else A = L L^H ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+tpbtf2(int up, i64 n, i64 kd, T *__restrict__ ab, i64 ldab, int *__restrict__ d_info)
+{
+    typedef Num<T> N;
+    typedef typename N::real R;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // S(i, c) for i <= c: 'U' ab[(kd + i - c) + c*ldab]; 'L' holds its conjugate at ab[(c - i) + i*ldab]
+    for (i64 j = 0; j < n; ++j) {
+        T *dj = ab + (up ? kd : 0) + j * ldab;
+        const R ajj = reinterpret_cast<const R *>(dj)[0];  // real part of the diagonal entry (xPBTF2 reads nothing else of it)
+        if (!(ajj > (R)0)) {  // xPBTF2: AJJ <= 0 (NaN continues in LAPACK; a NaN pivot makes everything NaN either way)
+            if (ajj <= (R)0) { if (tid == 0) d_info[0] = (int)(j + 1); return; }
+        }
+        const R d = sqrt(ajj), rinv = (R)1 / d;
+        const i64 kn = kd < n - 1 - j ? kd : n - 1 - j;
+        __syncthreads();  // everyone has read the pivot
+        if (tid == 0) { reinterpret_cast<R *>(dj)[0] = d; if (sizeof(T) != sizeof(R)) reinterpret_cast<R *>(dj)[1] = (R)0; }
+        // scale row j of U ('U') / column j of L ('L') by 1/d
+        for (i64 c = 1 + tid; c <= kn; c += nt) {
+            T *e = up ? ab + (kd - c) + (j + c) * ldab : ab + c + j * ldab;
+            R *er = reinterpret_cast<R *>(e);
+            er[0] *= rinv;
+            if (sizeof(T) != sizeof(R)) er[1] *= rinv;
+        }
+        __syncthreads();
+        // trailing update: 'U': S(j+r, j+c) -= conj(u_r) u_c (r <= c), u = row j;  'L': L(j+c, j+r) -= l_c conj(l_r) (c >= r), l = column j
+        const i64 total = kn * (kn + 1) / 2;
+        for (i64 e = tid; e < total; e += nt) {
+            i64 c = 1;
+            while (c * (c + 1) / 2 <= e) ++c;
+            const i64 r = e - c * (c - 1) / 2 + 1;
+            if (up) {
+                const T ur = ab[(kd - r) + (j + r) * ldab], uc = ab[(kd - c) + (j + c) * ldab];
+                T *t = ab + (kd + r - c) + (j + c) * ldab;
+                *t = N::fma(N::neg(N::conj(ur)), uc, *t);
+                if (r == c) *t = N::realpart(*t);
+            } else {
+                const T lr = ab[r + j * ldab], lc = ab[c + j * ldab];
+                T *t = ab + (c - r) + (j + r) * ldab;
+                *t = N::fma(N::neg(lc), N::conj(lr), *t);
+                if (r == c) *t = N::realpart(*t);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- banded x banded, banded x dense for the other element types: one thread per entry of C, inner index ascending ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+tgbmm_bb(i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 Cu, T alpha, const T *__restrict__ a, i64 lda, const T *__restrict__ b,
+         i64 ldb, T beta, T *__restrict__ c, i64 ldc)
+{
+    typedef Num<T> N;
+    const i64 W = Cl + Cu + 1, total = W * m;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 j = e / W, r = e - j * W, k = j + r - Cu;
+        if (k < 0 || k >= n) continue;
+        T *cp = c + r + j * ldc;
+        T acc = N::iszero(beta) ? N::zero() : N::mul(beta, *cp);
+        if (!N::iszero(alpha)) {
+            i64 v0 = k - Al > j - Bu ? k - Al : j - Bu, v1 = k + Au < j + Bl ? k + Au : j + Bl;
+            if (v0 < 0) v0 = 0;
+            if (v1 > nu - 1) v1 = nu - 1;
+            for (i64 v = v0; v <= v1; ++v) acc = N::fma(N::mul(alpha, b[(Bu + v - j) + j * ldb]), a[(Au + k - v) + v * lda], acc);
+        }
+        *cp = acc;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+tgbmm_bd(int op, i64 m, i64 n, i64 kl, i64 ku, i64 nrhs, T alpha, const T *__restrict__ a, i64 lda, const T *__restrict__ b, i64 ldb, T beta,
+         T *__restrict__ c, i64 ldc)
+{
+    typedef Num<T> N;
+    const i64 rows = op == 0 ? m : n, total = rows * nrhs;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 q = e / rows, i = e - q * rows;
+        T *cp = c + i + q * ldc;
+        const T *bq = b + q * ldb;
+        T acc = N::iszero(beta) ? N::zero() : N::mul(beta, *cp);
+        if (!N::iszero(alpha)) {
+            if (op == 0) {
+                const i64 j0 = i - kl > 0 ? i - kl : 0, j1 = i + ku < n - 1 ? i + ku : n - 1;
+                for (i64 j = j0; j <= j1; ++j) acc = N::fma(N::mul(alpha, bq[j]), a[(ku + i - j) + j * lda], acc);
+            } else {  // row i of op(A) = column i of A
+                const i64 r0 = i - ku > 0 ? i - ku : 0, r1 = i + kl < m - 1 ? i + kl : m - 1;
+                const T *col = a + i * lda + (ku - i);
+                T t = N::zero();
+                for (i64 r = r0; r <= r1; ++r) t = N::fma(op == 2 ? N::conj(col[r]) : col[r], bq[r], t);
+                acc = N::fma(alpha, t, acc);
+            }
+        }
+        *cp = acc;
+    }
+}
+
 template <typename T> __host__ T host_scalar(const void *p);
 template <> __host__ float host_scalar<float>(const void *p) { return *(const float *)p; }
 template <> __host__ double host_scalar<double>(const void *p) { return *(const double *)p; }
@@ -456,6 +630,138 @@ int gbtrs_impl(bmb200_ctx *h, char trans, i64 n, i64 kl, i64 ku, i64 nrhs, const
     return 0;
 }
 
+static int tb_op(char trans) { return (trans == 'N' || trans == 'n') ? 0 : ((trans == 'T' || trans == 't') ? 1 : ((trans == 'C' || trans == 'c') ? 2 : -1)); }
+
+template <typename T>
+int tb_impl(bmb200_ctx *h, bool solve, char uplo, char trans, char diag, i64 n, i64 k, const void *dA, i64 lda, void *dx, i64 incx)
+{
+    if (!h) return -1;
+    const int up = (uplo == 'U' || uplo == 'u'), unit = (diag == 'U' || diag == 'u'), op = tb_op(trans);
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -2;
+    if (op < 0) return -3;
+    if (!unit && !(diag == 'N' || diag == 'n')) return -4;
+    if (n < 0) return -5;
+    if (k < 0) return -6;
+    if (lda < k + 1) return -8;
+    if (incx != 1) return -10;
+    if (n == 0) return 0;
+    if (!dA || !dx) return -7;
+    DeviceGuard g(h->device);
+    if (solve) {
+        ttbsv<T><<<1, 256, 0, h->stream>>>(up, op, unit, n, k, (const T *)dA, lda, (T *)dx, n);
+        BMB_LAUNCH_CHECK(h);
+        return 0;
+    }
+    if (bmb_ensure_scratch(h, (size_t)n * sizeof(T)) != 0) return BMB200_ERR_CUDA;
+    const i64 blocks = imin64(cdiv64(n, 256), (i64)h->sm_count * 16);
+    ttbmv<T><<<(unsigned)blocks, 256, 0, h->stream>>>(up, op, unit, n, k, (const T *)dA, lda, (const T *)dx, (T *)h->scratch);
+    BMB_LAUNCH_CHECK(h);
+    BMB_CUDA(h, cudaMemcpyAsync(dx, h->scratch, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+template <typename T>
+int pbtrf_impl(bmb200_ctx *h, char uplo, i64 n, i64 kd, void *dAB, i64 ldab, int *info)
+{
+    if (!h) return -1;
+    const int up = (uplo == 'U' || uplo == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -2;
+    if (n < 0) return -3;
+    if (kd < 0) return -4;
+    if (ldab < kd + 1) return -6;
+    if (!info) return -7;
+    *info = 0;
+    if (n == 0) return 0;
+    if (!dAB) return -5;
+    DeviceGuard g(h->device);
+    int *d_info = h->d_info + 28;
+    BMB_CUDA(h, cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
+    tpbtf2<T><<<1, 256, 0, h->stream>>>(up, n, kd > n - 1 ? (n > 1 ? n - 1 : 0) : kd, (T *)dAB + (up ? kd - (kd > n - 1 ? (n > 1 ? n - 1 : 0) : kd) : 0), ldab, d_info);
+    BMB_LAUNCH_CHECK(h);
+    BMB_CUDA(h, cudaMemcpyAsync(info, d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    BMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename T>
+int pbtrs_impl(bmb200_ctx *h, char uplo, i64 n, i64 kd, i64 nrhs, const void *dAB, i64 ldab, void *dB, i64 ldb)
+{
+    if (!h) return -1;
+    const int up = (uplo == 'U' || uplo == 'u');
+    if (!up && !(uplo == 'L' || uplo == 'l')) return -2;
+    if (n < 0) return -3;
+    if (kd < 0) return -4;
+    if (nrhs < 0) return -5;
+    if (ldab < kd + 1) return -7;
+    if (ldb < (n > 1 ? n : 1)) return -9;
+    if (n == 0 || nrhs == 0) return 0;
+    if (!dAB || !dB) return -6;
+    DeviceGuard g(h->device);
+    // xPBTRS: 'U': U^H y = b, U x = y;  'L': L y = b, L^H x = y
+    ttbsv<T><<<(unsigned)nrhs, 256, 0, h->stream>>>(up, up ? 2 : 0, 0, n, kd, (const T *)dAB, ldab, (T *)dB, ldb);
+    BMB_LAUNCH_CHECK(h);
+    ttbsv<T><<<(unsigned)nrhs, 256, 0, h->stream>>>(up, up ? 0 : 2, 0, n, kd, (const T *)dAB, ldab, (T *)dB, ldb);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
+template <typename T>
+int gbmm_bb_impl(bmb200_ctx *h, i64 n, i64 nu, i64 m, i64 Al, i64 Au, i64 Bl, i64 Bu, i64 Cl, i64 Cu, const void *alpha, const void *dA, i64 lda,
+                 const void *dB, i64 ldb, const void *beta, void *dC, i64 ldc)
+{
+    if (!h) return -1;
+    if (n < 0) return -2;
+    if (nu < 0) return -3;
+    if (m < 0) return -4;
+    if (Al < 0) return -5;
+    if (Au < 0) return -6;
+    if (Bl < 0) return -7;
+    if (Bu < 0) return -8;
+    if (Cl < 0 || Cl > Al + Bl) return -9;
+    if (Cu < 0 || Cu > Au + Bu) return -10;
+    if (!alpha) return -11;
+    if (lda < Al + Au + 1) return -13;
+    if (ldb < Bl + Bu + 1) return -15;
+    if (!beta) return -16;
+    if (ldc < Cl + Cu + 1) return -18;
+    if (n == 0 || m == 0) return 0;
+    if (!dC || (nu > 0 && (!dA || !dB))) return -12;
+    DeviceGuard g(h->device);
+    const i64 blocks = imin64(cdiv64((Cl + Cu + 1) * m, 256), (i64)h->sm_count * 16);
+    tgbmm_bb<T><<<(unsigned)blocks, 256, 0, h->stream>>>(n, nu, m, Al, Au, Bl, Bu, Cl, Cu, host_scalar<T>(alpha), (const T *)dA, lda, (const T *)dB, ldb,
+                                                         host_scalar<T>(beta), (T *)dC, ldc);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
+template <typename T>
+int gbmm_bd_impl(bmb200_ctx *h, char trans, i64 m, i64 n, i64 kl, i64 ku, i64 nrhs, const void *alpha, const void *dA, i64 lda, const void *dB, i64 ldb,
+                 const void *beta, void *dC, i64 ldc)
+{
+    if (!h) return -1;
+    const int op = tb_op(trans);
+    if (op < 0) return -2;
+    if (m < 0) return -3;
+    if (n < 0) return -4;
+    if (kl < 0) return -5;
+    if (ku < 0) return -6;
+    if (nrhs < 0) return -7;
+    if (!alpha) return -8;
+    if (lda < kl + ku + 1) return -10;
+    const i64 rowsB = op ? m : n, rowsC = op ? n : m;
+    if (ldb < imax64(1, rowsB)) return -12;
+    if (!beta) return -13;
+    if (ldc < imax64(1, rowsC)) return -15;
+    if (rowsC == 0 || nrhs == 0) return 0;
+    if (!dC || (rowsB > 0 && (!dA || !dB))) return -9;
+    DeviceGuard g(h->device);
+    const i64 blocks = imin64(cdiv64(rowsC * nrhs, 256), (i64)h->sm_count * 16);
+    tgbmm_bd<T><<<(unsigned)blocks, 256, 0, h->stream>>>(op, m, n, kl, ku, nrhs, host_scalar<T>(alpha), (const T *)dA, lda, (const T *)dB, ldb,
+                                                         host_scalar<T>(beta), (T *)dC, ldc);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
 }  // namespace
 
 #define BMB_TYPED_EXPORTS(P, T)                                                                                                                   \
@@ -478,6 +784,41 @@ int gbtrs_impl(bmb200_ctx *h, char trans, i64 n, i64 kl, i64 ku, i64 nrhs, const
 BMB_TYPED_EXPORTS(s, float)
 BMB_TYPED_EXPORTS(c, cuFloatComplex)
 BMB_TYPED_EXPORTS(z, cuDoubleComplex)
+
+#define BMB_TYPED_EXPORTS2(P, T)                                                                                                                     \
+    extern "C" int bmb200_##P##tbsv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const void *dA, int64_t lda, void *dx,  \
+                                    int64_t incx)                                                                                                    \
+    {                                                                                                                                                \
+        return tb_impl<T>(h, true, uplo, trans, diag, n, k, dA, lda, dx, incx);                                                                      \
+    }                                                                                                                                                \
+    extern "C" int bmb200_##P##tbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const void *dA, int64_t lda, void *dx,  \
+                                    int64_t incx)                                                                                                    \
+    {                                                                                                                                                \
+        return tb_impl<T>(h, false, uplo, trans, diag, n, k, dA, lda, dx, incx);                                                                     \
+    }                                                                                                                                                \
+    extern "C" int bmb200_##P##pbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, void *dAB, int64_t ldab, int *info)                          \
+    {                                                                                                                                                \
+        return pbtrf_impl<T>(h, uplo, n, kd, dAB, ldab, info);                                                                                       \
+    }                                                                                                                                                \
+    extern "C" int bmb200_##P##pbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t nrhs, const void *dAB, int64_t ldab, void *dB,       \
+                                     int64_t ldb)                                                                                                    \
+    {                                                                                                                                                \
+        return pbtrs_impl<T>(h, uplo, n, kd, nrhs, dAB, ldab, dB, ldb);                                                                              \
+    }                                                                                                                                                \
+    extern "C" int bmb200_##P##gbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t m, int64_t Al, int64_t Au, int64_t Bl, int64_t Bu, int64_t Cl, \
+                                       int64_t Cu, const void *alpha, const void *dA, int64_t lda, const void *dB, int64_t ldb, const void *beta,     \
+                                       void *dC, int64_t ldc)                                                                                        \
+    {                                                                                                                                                \
+        return gbmm_bb_impl<T>(h, n, nu, m, Al, Au, Bl, Bu, Cl, Cu, alpha, dA, lda, dB, ldb, beta, dC, ldc);                                         \
+    }                                                                                                                                                \
+    extern "C" int bmb200_##P##gbmm_bd(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, int64_t nrhs, const void *alpha,   \
+                                       const void *dA, int64_t lda, const void *dB, int64_t ldb, const void *beta, void *dC, int64_t ldc)             \
+    {                                                                                                                                                \
+        return gbmm_bd_impl<T>(h, trans, m, n, kl, ku, nrhs, alpha, dA, lda, dB, ldb, beta, dC, ldc);                                                \
+    }
+BMB_TYPED_EXPORTS2(s, float)
+BMB_TYPED_EXPORTS2(c, cuFloatComplex)
+BMB_TYPED_EXPORTS2(z, cuDoubleComplex)
 
 // the generic kernels instantiated for double: a cross-check of the tuned Float64 path (tests), not a dispatch target
 extern "C" int bmb200_internal_dgbtrf_generic(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, double *dAB, int64_t ldab, int64_t *d_ipiv, int *info)

@@ -509,6 +509,8 @@ def _tb(fn_name: str, uplo: str, trans: str, diag: str, m: int, k: int, Adata: t
         return x
     hd = _h(x)
     lda = max(1, Adata.stride(0)) if n > 1 else max(1, Adata.shape[1])
+    p = _typed(Adata, x)  # Float64 keeps its tuned kernels; S / C / Z run the generic ones (same argument list)
+    fn_name = fn_name.replace("bmb200_d", f"bmb200_{p}")
     rc = getattr(hd.lib, fn_name)(hd.h, uplo.encode(), trans.encode(), diag.encode(), n, k, vp(Adata.data_ptr()), lda,
                                   vp(x.data_ptr()), 1)
     hd.check(rc, fn_name[7:])
@@ -614,7 +616,7 @@ def pbtrf_(uplo: str, m: int, kd: int, Adata: torch.Tensor):
     hd = _h(Adata)
     lda = max(1, Adata.stride(0)) if n > 1 else max(1, Adata.shape[1])
     info = C.c_int(0)
-    rc = hd.lib.bmb200_dpbtrf(hd.h, uplo.encode(), n, kd, vp(Adata.data_ptr()), lda, C.byref(info))
+    rc = getattr(hd.lib, f"bmb200_{_typed(Adata)}pbtrf")(hd.h, uplo.encode(), n, kd, vp(Adata.data_ptr()), lda, C.byref(info))
     if rc < 0 and rc > -100:
         raise ValueError(f"invalid argument #{-rc} to LAPACK call")  # chkargsok
     hd.check(rc, "dpbtrf")
@@ -638,7 +640,7 @@ def pbtrs_(uplo: str, m: int, kd: int, Adata: torch.Tensor, B: torch.Tensor) -> 
     ldb = max(1, n) if B.dim() == 1 else _ld(B)
     hd = _h(B)
     lda = max(1, Adata.stride(0)) if n > 1 else max(1, Adata.shape[1])
-    rc = hd.lib.bmb200_dpbtrs(hd.h, uplo.encode(), n, kd, nrhs, vp(Adata.data_ptr()), lda, vp(B.data_ptr()), ldb)
+    rc = getattr(hd.lib, f"bmb200_{_typed(Adata, B)}pbtrs")(hd.h, uplo.encode(), n, kd, nrhs, vp(Adata.data_ptr()), lda, vp(B.data_ptr()), ldb)
     if rc < 0 and rc > -100:
         raise ValueError(f"invalid argument #{-rc} to LAPACK call")
     hd.check(rc, "dpbtrs")
@@ -755,6 +757,42 @@ def hbmv_(uplo: str, k: int, alpha, Adata: torch.Tensor, x: torch.Tensor, beta, 
                                vp(be.ctypes.data), vp(y.data_ptr()), 1)
     hd.check(rc, name[7:])
     return y
+
+
+def gbmm_typed_(alpha, Adata: torch.Tensor, Bdata: torch.Tensor, beta, Cdata: torch.Tensor, sizes, Ab, Bb, Cb) -> torch.Tensor:
+    """``_gbmm!(alpha, A_data, B_data, beta, C_data, (n, nu, m), (Al, Au), (Bl, Bu), (Cl, Cu))`` (src/banded/gbmm.jl:296-340) on
+    band arrays of any of the four element types ((ncols, rows) tensors)."""
+    p = _typed(Adata, Bdata, Cdata)
+    n, nu, m = sizes
+    hd = _h(Cdata)
+    if p == "d":
+        rc = hd.lib.bmb200_dgbmm_bb(hd.h, n, nu, m, Ab[0], Ab[1], Bb[0], Bb[1], Cb[0], Cb[1], float(alpha), vp(Adata.data_ptr()), _lda_of(Adata),
+                                    vp(Bdata.data_ptr()), _lda_of(Bdata), float(beta), vp(Cdata.data_ptr()), _lda_of(Cdata))
+    else:
+        al, be = _host_scalar(Adata.dtype, alpha), _host_scalar(Adata.dtype, beta)
+        rc = getattr(hd.lib, f"bmb200_{p}gbmm_bb")(hd.h, n, nu, m, Ab[0], Ab[1], Bb[0], Bb[1], Cb[0], Cb[1], vp(al.ctypes.data), vp(Adata.data_ptr()),
+                                                   _lda_of(Adata), vp(Bdata.data_ptr()), _lda_of(Bdata), vp(be.ctypes.data), vp(Cdata.data_ptr()),
+                                                   _lda_of(Cdata))
+    hd.check(rc, f"{p}gbmm_bb")
+    return Cdata
+
+
+def gbmm_bd_typed_(trans: str, m: int, kl: int, ku: int, alpha, Adata: torch.Tensor, B: torch.Tensor, beta, Cd: torch.Tensor) -> torch.Tensor:
+    """C <- alpha*op(A)*B + beta*C, A banded m x n, B / C dense column-major (the per-column mul! loop of
+    src/generic/matmul.jl:243-256) for any of the four element types."""
+    p = _typed(Adata, B, Cd)
+    n = Adata.shape[0]
+    hd = _h(Cd)
+    nrhs = B.shape[1]
+    if p == "d":
+        rc = hd.lib.bmb200_dgbmm_bd(hd.h, trans.encode(), m, n, kl, ku, nrhs, float(alpha), vp(Adata.data_ptr()), _lda_of(Adata), vp(B.data_ptr()),
+                                    _ld(B), float(beta), vp(Cd.data_ptr()), _ld(Cd))
+    else:
+        al, be = _host_scalar(Adata.dtype, alpha), _host_scalar(Adata.dtype, beta)
+        rc = getattr(hd.lib, f"bmb200_{p}gbmm_bd")(hd.h, trans.encode(), m, n, kl, ku, nrhs, vp(al.ctypes.data), vp(Adata.data_ptr()), _lda_of(Adata),
+                                                   vp(B.data_ptr()), _ld(B), vp(be.ctypes.data), vp(Cd.data_ptr()), _ld(Cd))
+    hd.check(rc, f"{p}gbmm_bd")
+    return Cd
 
 
 def gbtrf_(m: int, kl: int, ku: int, AB: torch.Tensor):

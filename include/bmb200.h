@@ -175,6 +175,48 @@ int bmb200_zgbtrf(bmb200_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t k
                   int64_t *d_ipiv, int *info);
 int bmb200_zgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t kl, int64_t ku, int64_t nrhs, const void *dAB,
                   int64_t ldab, const int64_t *d_ipiv, void *dB, int64_t ldb);
+/* the remaining S / C / Z entry points of the path (tbsv! / tbmv! src/blas.jl:71-141, pbtrf! / pbtrs! src/lapack.jl:268-332 with
+ * Hermitian semantics for the complex types, _gbmm! src/banded/gbmm.jl:296-340 and the banded x dense loop
+ * src/generic/matmul.jl:243-256): same argument lists as the d-routines, generic kernels (typed.cu), equal to OpenBLAS to rounding. */
+int bmb200_stbsv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const void *dA, int64_t lda,
+                 void *dx, int64_t incx);
+int bmb200_stbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const void *dA, int64_t lda,
+                 void *dx, int64_t incx);
+int bmb200_spbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, void *dAB, int64_t ldab, int *info);
+int bmb200_spbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t nrhs, const void *dAB, int64_t ldab, void *dB,
+                  int64_t ldb);
+int bmb200_sgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t m, int64_t Al, int64_t Au, int64_t Bl, int64_t Bu,
+                    int64_t Cl, int64_t Cu, const void *alpha, const void *dA, int64_t lda, const void *dB, int64_t ldb,
+                    const void *beta, void *dC, int64_t ldc);
+int bmb200_sgbmm_bd(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, int64_t nrhs,
+                    const void *alpha, const void *dA, int64_t lda, const void *dB, int64_t ldb, const void *beta, void *dC,
+                    int64_t ldc);
+int bmb200_ctbsv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const void *dA, int64_t lda,
+                 void *dx, int64_t incx);
+int bmb200_ctbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const void *dA, int64_t lda,
+                 void *dx, int64_t incx);
+int bmb200_cpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, void *dAB, int64_t ldab, int *info);
+int bmb200_cpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t nrhs, const void *dAB, int64_t ldab, void *dB,
+                  int64_t ldb);
+int bmb200_cgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t m, int64_t Al, int64_t Au, int64_t Bl, int64_t Bu,
+                    int64_t Cl, int64_t Cu, const void *alpha, const void *dA, int64_t lda, const void *dB, int64_t ldb,
+                    const void *beta, void *dC, int64_t ldc);
+int bmb200_cgbmm_bd(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, int64_t nrhs,
+                    const void *alpha, const void *dA, int64_t lda, const void *dB, int64_t ldb, const void *beta, void *dC,
+                    int64_t ldc);
+int bmb200_ztbsv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const void *dA, int64_t lda,
+                 void *dx, int64_t incx);
+int bmb200_ztbmv(bmb200_handle_t h, char uplo, char trans, char diag, int64_t n, int64_t k, const void *dA, int64_t lda,
+                 void *dx, int64_t incx);
+int bmb200_zpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, void *dAB, int64_t ldab, int *info);
+int bmb200_zpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t nrhs, const void *dAB, int64_t ldab, void *dB,
+                  int64_t ldb);
+int bmb200_zgbmm_bb(bmb200_handle_t h, int64_t n, int64_t nu, int64_t m, int64_t Al, int64_t Au, int64_t Bl, int64_t Bu,
+                    int64_t Cl, int64_t Cu, const void *alpha, const void *dA, int64_t lda, const void *dB, int64_t ldb,
+                    const void *beta, void *dC, int64_t ldc);
+int bmb200_zgbmm_bd(bmb200_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, int64_t nrhs,
+                    const void *alpha, const void *dA, int64_t lda, const void *dB, int64_t ldb, const void *beta, void *dC,
+                    int64_t ldc);
 /* symmetric (Float32) / Hermitian (complex) band matvec from one stored triangle: ssbmv_ / chbmv_ / zhbmv_ reached through
  * sbmv! / hbmv! (src/blas.jl:36-66), i.e. mul! of Symmetric / Hermitian{<:BandedMatrix} (src/symbanded/symbanded.jl:72-96).
  * Only the real part of the diagonal is read, as in xHBMV.  incx = incy = 1; x must not alias y.                            */

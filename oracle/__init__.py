@@ -222,6 +222,24 @@ class _OpenBLASBackend:
         getattr(self.L, f"scipy_{p}gbtrs_64_")(C.c_char_p(trans.encode()), r(i64(n)), r(i64(kl)), r(i64(ku)), r(i64(nrhs)), _ptr(ab),
                                               r(i64(ldab)), _ptr(ipiv), _ptr(b), r(i64(ldb)), r(info), C.c_long(1))
         return int(info.value)
+    def t_tb(self, name, uplo, trans, diag, n, k, a, lda, x):  # {s,c,z}tbsv_ / tbmv_ as src/blas.jl:94-99, 132-137 call them
+        p, r = self.prefix(a.dtype), C.byref
+        getattr(self.L, f"scipy_{p}{name}_64_")(C.c_char_p(uplo.encode()), C.c_char_p(trans.encode()), C.c_char_p(diag.encode()), r(i64(n)), r(i64(k)),
+                                               _ptr(a), r(i64(lda)), _ptr(x), r(i64(1)), C.c_long(1), C.c_long(1), C.c_long(1))
+        return 0
+
+    def t_pbtrf(self, uplo, n, kd, ab, ldab):
+        p, r = self.prefix(ab.dtype), C.byref
+        info = i64(0)
+        getattr(self.L, f"scipy_{p}pbtrf_64_")(C.c_char_p(uplo.encode()), r(i64(n)), r(i64(kd)), _ptr(ab), r(i64(ldab)), r(info), C.c_long(1))
+        return int(info.value)
+
+    def t_pbtrs(self, uplo, n, kd, nrhs, ab, ldab, b, ldb):
+        p, r = self.prefix(ab.dtype), C.byref
+        info = i64(0)
+        getattr(self.L, f"scipy_{p}pbtrs_64_")(C.c_char_p(uplo.encode()), r(i64(n)), r(i64(kd)), r(i64(nrhs)), _ptr(ab), r(i64(ldab)), _ptr(b),
+                                              r(i64(ldb)), r(info), C.c_long(1))
+        return int(info.value)
 
 
 _backends: dict = {}

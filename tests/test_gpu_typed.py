@@ -136,3 +136,95 @@ def test_typed_singular_info_and_type_errors(bm):
     with pytest.raises(TypeError):
         bm.gbmv_("N", 4, 1, 1, 1.0, torch.zeros((4, 3), dtype=torch.float32, device="cuda"), torch.zeros(4, dtype=torch.float64, device="cuda"), 0.0,
                  torch.zeros(4, dtype=torch.float32, device="cuda"))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(1, 0), (6, 2), (300, 3), (500, 17), (40, 60), (3000, 5)])
+def test_typed_tbsv_tbmv(bm, oracle_ob, rng, dt, shape):
+    """tbsv! / tbmv! (src/blas.jl:71-141) for S / C / Z, all of uplo x trans x diag, against OpenBLAS' own entry points."""
+    n, k = shape
+    for uplo, trans, diag in itertools.product("UL", "NTC", "NU"):
+        a = _rand(rng, (k + 1, n), dt) / (2 * k + 2)
+        a[k if uplo == "U" else 0, :] = (1.5 + rng.random(n)).astype(dt)
+        dA = _dev(a)
+        for name, fn in (("tbsv", bm.tbsv_), ("tbmv", bm.tbmv_)):
+            x0 = _rand(rng, n, dt)
+            ref = x0.copy()
+            oracle_ob.t_tb(name, uplo, trans, diag, n, k, a, k + 1, ref)
+            x = torch.as_tensor(x0.copy()).cuda()
+            fn(uplo, trans, diag, n, k, dA, x)
+            assert _close(x.cpu().numpy(), ref, dt) or float(np.max(np.abs(x.cpu().numpy() - ref))) <= 20 * TOL[dt] * max(1.0, float(np.max(np.abs(ref)))), (
+                dt, name, uplo, trans, diag, shape)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(1, 0), (8, 2), (300, 4), (400, 33), (30, 40), (2000, 3)])
+def test_typed_pbtrf_pbtrs(bm, oracle_ob, rng, dt, shape):
+    """pbtrf! / pbtrs! (src/lapack.jl:268-332) for S / C / Z: Hermitian positive definite bands, both triangles."""
+    n, kd = shape
+    for uplo in "UL":
+        ab = _rand(rng, (kd + 1, n), dt)
+        ab[kd if uplo == "U" else 0, :] = (2.0 * (kd + 1) + rng.random(n)).astype(dt)  # real, dominant diagonal
+        ref = ab.copy(order="F")
+        assert oracle_ob.t_pbtrf(uplo, n, kd, ref, kd + 1) == 0
+        dA = _dev(ab)
+        _, info = bm.pbtrf_(uplo, n, kd, dA)
+        assert info == 0
+        got = _host(dA)
+        mask = np.zeros((kd + 1, n), dtype=bool)
+        for d in range(kd + 1):
+            if uplo == "U":
+                mask[kd - d, d:] = True
+            else:
+                mask[d, : n - d] = True
+        assert float(np.max(np.abs(got[mask] - ref[mask]))) <= 20 * TOL[dt] * float(np.max(np.abs(ref[mask]))), (dt, uplo, shape)
+        b = _rand(rng, (n, 2), dt)
+        bref = b.copy(order="F")
+        assert oracle_ob.t_pbtrs(uplo, n, kd, 2, ref, kd + 1, bref, n) == 0
+        dB = torch.as_tensor(np.ascontiguousarray(b.T)).cuda().T
+        bm.pbtrs_(uplo, n, kd, dA, dB)
+        assert float(np.max(np.abs(dB.cpu().numpy() - bref))) <= 50 * TOL[dt] * max(1.0, float(np.max(np.abs(bref)))), (dt, uplo, shape)
+    # not positive definite
+    ab = _rand(rng, (kd + 1, n), dt)
+    ab[kd, :] = (2.0 * (kd + 1)).real if False else 2.0 * (kd + 1)
+    if n > 3:
+        ab[kd, n // 2] = -1.0
+        _, info = bm.pbtrf_("U", n, kd, _dev(ab))
+        assert info == n // 2 + 1
+
+
+def _band_dense(a, m, n, l, u):
+    D = np.zeros((m, n), dtype=a.dtype)
+    for j in range(n):
+        for i in range(max(0, j - u), min(m, j + l + 1)):
+            D[i, j] = a[u + i - j, j]
+    return D
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(40, 40, 40, 2, 1, 1, 3), (120, 100, 90, 4, 3, 5, 2), (60, 70, 80, 0, 3, 2, 0), (200, 200, 200, 17, 9, 12, 20)])
+def test_typed_gbmm(bm, rng, dt, shape):
+    """banded x banded (_gbmm!, src/banded/gbmm.jl:296-340) and banded x dense (src/generic/matmul.jl:243-256) for S / C / Z against a
+    dense numpy product in the next higher precision."""
+    n, nu, m, Al, Au, Bl, Bu = shape
+    hi = np.complex128 if np.issubdtype(dt, np.complexfloating) else np.float64
+    alpha, beta = (0.75 - 0.5j, -0.5 + 0.25j) if np.issubdtype(dt, np.complexfloating) else (0.75, -0.5)
+    a, b = _rand(rng, (Al + Au + 1, nu), dt), _rand(rng, (Bl + Bu + 1, m), dt)
+    Cl, Cu = min(n - 1, Al + Bl), min(m - 1, Au + Bu)
+    c0 = _rand(rng, (Cl + Cu + 1, m), dt)
+    DA, DB, DC = _band_dense(a, n, nu, Al, Au).astype(hi), _band_dense(b, nu, m, Bl, Bu).astype(hi), _band_dense(c0, n, m, Cl, Cu).astype(hi)
+    ref = alpha * (DA @ DB) + beta * DC
+    dC = _dev(c0)
+    bm.gbmm_typed_(alpha, _dev(a), _dev(b), beta, dC, (n, nu, m), (Al, Au), (Bl, Bu), (Cl, Cu))
+    got = _band_dense(_host(dC), n, m, Cl, Cu)
+    inband = _band_dense(np.ones((Cl + Cu + 1, m), dtype=dt), n, m, Cl, Cu) != 0
+    assert float(np.max(np.abs(got[inband] - ref[inband]))) <= 20 * TOL[dt] * float(np.max(np.abs(ref))), (dt, shape)
+    # banded x dense, all three ops
+    for trans, op in (("N", DA), ("T", DA.T), ("C", DA.conj().T)):
+        X = _rand(rng, (op.shape[1], 5), dt)
+        Y0 = _rand(rng, (op.shape[0], 5), dt)
+        refy = alpha * (op @ X.astype(hi)) + beta * Y0.astype(hi)
+        dX = torch.as_tensor(np.ascontiguousarray(X.T)).cuda().T
+        dY = torch.as_tensor(np.ascontiguousarray(Y0.T)).cuda().T
+        bm.gbmm_bd_typed_(trans, n, Al, Au, alpha, _dev(a), dX, beta, dY)
+        assert float(np.max(np.abs(dY.cpu().numpy() - refy))) <= 20 * TOL[dt] * float(np.max(np.abs(refy))), (dt, trans, shape)
