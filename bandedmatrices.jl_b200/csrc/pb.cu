@@ -173,6 +173,66 @@ pbtf2_window(i64 n_total, int kd_total, int blocked, i64 si, i64 sk, double *__r
     }
 }
 
+// ---- kd <= 31: DPBTF2 on ONE warp, register resident, no shared memory and no barrier.  Lane d owns diagonal d: it holds
+// S(i, i+d) for the kd+1 live rows i = j .. j+kd in W[i mod (KD+1)] (the j loop is unrolled KD+1 times, so every register index is
+// static) and, in Q, the same slots one window ahead (rows are fetched KD+1 steps before they are needed).  Step j: the pivot is
+// lane 0's entry of row j (one shuffle), every lane takes sqrt and reciprocal itself, x_d = S(j,j+d)/sqrt is ALREADY in lane d;
+// entry S(j+r, j+r+d) -= x_{r+d} x_r needs one broadcast (x_r) and one shift (x_{r+d}) per r.  Per column the dependency chain is
+// shuffle + sqrt + divide + multiply + one shared-memory post + FMA; in practice the single warp is bound by its instruction
+// count (~700 cycles per column at kd = 4, ~40 more per extra diagonal), so dispatch uses it for kd <= 8 only.  The
+// order per entry is DPBTF2's (ascending j, t = -x_c rounded, zero x_c skipped): factors stay bit-identical to OpenBLAS.  After
+// a non-positive pivot the warp goes `dead`: x = 0 (no update does anything), rows are written back as they stand.
+template <int KD>
+__global__ void __launch_bounds__(32)
+pbtf2_diag(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state)
+{
+    constexpr int NS = KD + 1;
+    const int lane = threadIdx.x;
+    const i64 dstep = si + sk;                       // S(i,i+d) = p0[i*dstep + d*sk]
+    double *base = p0 + (i64)lane * sk;
+    const bool mine = lane <= kd;
+    auto fetch = [&](i64 i) { return (mine && i + lane < n) ? base[i * dstep] : 0.0; };
+    __shared__ double xs[2][64];
+    xs[0][lane] = xs[1][lane] = 0.0;
+    xs[0][32 + lane] = xs[1][32 + lane] = 0.0;
+    __syncwarp();
+    double W[NS], Q[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { W[s] = fetch(s); Q[s] = fetch(s + NS); }
+    bool dead = false;
+    int info = 0;
+    for (i64 jb = 0; jb < n; jb += NS) {
+#pragma unroll
+        for (int ph = 0; ph < NS; ++ph) {
+            const i64 j = jb + ph;
+            if (j < n) {  // warp-uniform
+                const double v = W[ph];
+                const double ajj = __shfl_sync(0xffffffffu, v, 0);
+                if (!dead && ajj <= 0.0) { dead = true; info = (int)(j + 1); }
+                const double dj = sqrt(ajj), rinv = 1.0 / dj;
+                const double x = dead ? 0.0 : __dmul_rn(v, rinv);
+                const int kn = (int)imin64_d(kd, n - 1 - j);
+                if (lane <= kn) base[j * dstep] = dead ? v : (lane == 0 ? dj : x);
+                // every lane needs the whole scaled row: x_r (same for all lanes) and x_{r+d} (a shift).  One shared-memory post per
+                // step (double-buffered by step parity, entries 32..63 stay 0) and two loads per r -- four SHFL per r from this single
+                // warp measured ~70 cycles per r, batched or not (shuffles from one warp do not pipeline)
+                double *xb = xs[ph & 1];
+                xb[lane] = x;
+                __syncwarp();
+#pragma unroll
+                for (int r = 1; r <= KD; ++r) {
+                    const double xr = xb[r], xc = xb[lane + r];
+                    const int slot = (ph + r) % NS;
+                    if (lane + r <= kn && xc != 0.0) W[slot] = fma(-xc, xr, W[slot]);
+                }
+                W[ph] = Q[ph];
+                Q[ph] = fetch(j + 2 * NS);
+            }
+        }
+    }
+    if (lane == 0 && info) d_state[0] = info;
+}
+
 // K1 of the blocked path: Cholesky of the NB x NB diagonal block, REGISTER resident.  Thread (a, b) = (tid / 16, tid % 16)
 // owns the 4 x 4 patch rows 4a.., columns 4b.. (patches below the diagonal idle).  Step j = 4*jb + u (u unrolled, so every
 // register index is static): the 16 lanes with a == jb sit in one warp -- the pivot comes by one shuffle from the diagonal
@@ -558,7 +618,16 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
         dstats = (long long *)((char *)h->scratch + 2048);
         BMB_CUDA(h, cudaMemsetAsync(dstats, 0, 8 * sizeof(long long), h->stream));
     }
-    if (!blocked) {
+    // measured (n = 2^20, ns per column, one-warp kernel / window kernel): kd = 4: 358 / 437, 8: 548 / ~600, 16: 610 / 562,
+    // 31: 1222 / ~750 -- a single warp pays ~40 cycles per extra diagonal, so it only takes the narrowest bands
+    const bool force_diag = h->tune.pb_nodiag == -1 && kd <= 31;
+    if (!blocked && (kd <= 8 || force_diag) && h->tune.pb_nodiag != 1) {
+        if (kd <= 4) pbtf2_diag<4><<<1, 32, 0, h->stream>>>(n, (int)kd, si, sk, p0, d_state);
+        else if (kd <= 8) pbtf2_diag<8><<<1, 32, 0, h->stream>>>(n, (int)kd, si, sk, p0, d_state);
+        else if (kd <= 16) pbtf2_diag<16><<<1, 32, 0, h->stream>>>(n, (int)kd, si, sk, p0, d_state);
+        else pbtf2_diag<31><<<1, 32, 0, h->stream>>>(n, (int)kd, si, sk, p0, d_state);
+        BMB_LAUNCH_CHECK(h);
+    } else if (!blocked) {
         const int kdw = (int)kd;
         int ring = 16, P = 8;
         while (ring < kdw + 1 + PB_PFD) ring <<= 1;

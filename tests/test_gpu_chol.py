@@ -38,8 +38,19 @@ def _sym_dense(ab, n, kd, uplo):
 
 @pytest.mark.parametrize("shape", [(1, 0), (2, 1), (7, 2), (40, 3), (1000, 4), (3000, 8), (2000, 9), (5000, 16), (1500, 17),
                                    (4000, 31), (2500, 32), (1200, 33), (900, 64), (20, 40), (64, 63), (30000, 5)])
-def test_pbtrf_pbtrs_narrow_bit_identical(bm, oracle_c, rng, shape):
+@pytest.mark.parametrize("diag_kernel", [0, -1, 1])
+def test_pbtrf_pbtrs_narrow_bit_identical(bm, oracle_c, rng, shape, diag_kernel):
+    """diag_kernel: tuning value of pb_nodiag -- 0 shipped dispatch, -1 the one-warp register kernel for every kd <= 31, 1 the
+    shared-memory window kernel for every kd <= 64: both kernels must reproduce DPBTF2 bit for bit."""
     n, kd = shape
+    bm.handle(0).tune("pb_nodiag", diag_kernel)
+    try:
+        _narrow_case(bm, oracle_c, rng, n, kd)
+    finally:
+        bm.handle(0).tune("reset", 0)
+
+
+def _narrow_case(bm, oracle_c, rng, n, kd):
     for uplo, extra in itertools.product("UL", (0, 3)):
         ab = _spd_band(rng, n, kd, uplo, extra)
         ldab = ab.shape[0]
@@ -100,7 +111,7 @@ def test_pbtrf_wide_blocked(bm, oracle_ob, rng, shape):
         assert np.max(np.abs(dB.cpu().numpy() - bref)) <= 1e-12 * max(1.0, np.max(np.abs(bref))), (uplo, n, kd)
 
 
-@pytest.mark.parametrize("kd", [3, 40, 100])
+@pytest.mark.parametrize("kd", [3, 7, 20, 40, 100])
 def test_pbtrf_not_positive_definite(bm, oracle_c, rng, kd):
     n = 400
     for uplo in "UL":

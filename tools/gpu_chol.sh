@@ -3,8 +3,6 @@
 mkdir -p gpurun_out
 exec > gpurun_out/chol.log 2>&1
 set -x
-timeout 600 python -m pytest tests/test_gpu_chol.py -m gpu -x -q 2>&1 | tail -12
-timeout 200 python tools/time_chol.py 1048576 16 U 256
-timeout 200 python tools/time_chol.py 1048576 16 L 16
+timeout 600 python -m pytest tests/test_gpu_chol.py -m gpu -x -q 2>&1 | tail -8
+timeout 200 python tools/time_chol.py 1048576 16 U 16
 timeout 200 python tools/time_chol.py 1048576 4 U 1
-timeout 200 python tools/time_chol.py 1048576 48 U 4
