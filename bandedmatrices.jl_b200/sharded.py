@@ -144,6 +144,28 @@ class ShardedSolve:
         return ldiv_(self.F, B_local)
 
 
+class ShardedCholeskySolve:
+    """``ldiv!(cholesky(Symmetric(A)), B)`` (src/symbanded/BandedCholesky.jl:72-80) with the columns of B sharded over the ranks,
+    like ``ShardedSolve``: the factorisation is one dependency chain and stays on rank ``src``; ONE broadcast of the
+    (n, kd+1) factor triangle, then every rank runs ``bmb200_dpbtrs`` on its block of right-hand sides, no exchange."""
+
+    def __init__(self, tri: torch.Tensor | None, uplo: str, n: int, kd: int, rank: int, world: int, group=None, src: int = 0, device=None):
+        self.rank, self.world, self.n, self.kd, self.uplo = rank, world, n, kd, uplo
+        if tri is None:
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            tri = torch.empty((n, kd + 1), dtype=torch.float64, device=dev)
+        elif not tri.is_contiguous():
+            tri = tri.contiguous()
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(tri, src, group=group)
+        self.tri = tri
+
+    def ldiv_(self, B_local: torch.Tensor) -> torch.Tensor:
+        from .linalg import pbtrs_
+
+        return pbtrs_(self.uplo, self.n, self.kd, self.tri, B_local)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # banded x banded, sharded over the COLUMNS of B and C (SURVEY.md 8e; reference _gbmm!, src/banded/gbmm.jl:296-340: column
 # j of C is one gbmv over A's columns [j-Bu, j+Bl]).  Rank r owns columns [j0, j1) of B and C and needs A's columns

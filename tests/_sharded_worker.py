@@ -51,6 +51,44 @@ def check_sharded_solve(backend, rank, world, C):
         assert np.array_equal(Xl.cpu().numpy(), ref[:, q0:q1]), ("sharded solve", rank)
 
 
+def check_sharded_cholesky_solve(backend, rank, world, C):
+    """RHS-sharded ldiv! of the banded Cholesky: factor triangle broadcast from rank 0, every rank solves its block of columns;
+    the blocks together are the oracle's DPBTRS solution (to rounding: the device runs both sweeps as column sweeps)."""
+    for uplo, n, kd in (("U", 2500, 4), ("L", 1800, 70)):
+        nrhs = 5 * world + 2
+        rng = np.random.default_rng(17)
+        ab = np.asfortranarray(rng.standard_normal((kd + 1, n)))
+        ab[kd if uplo == "U" else 0, :] = 2.0 * (kd + 1) + rng.random(n)
+        B = np.asfortranarray(rng.standard_normal((n, nrhs)))
+        fac = ab.copy(order="F")
+        assert C.pbtrf(uplo, n, kd, fac, kd + 1) == 0
+        ref = B.copy(order="F")
+        assert C.pbtrs(uplo, n, kd, nrhs, fac, kd + 1, ref, n) == 0
+        q0, q1 = rhs_bounds(nrhs, rank, world)
+        if backend == "gloo":
+            tri = torch.as_tensor(np.ascontiguousarray(fac.T)) if rank == 0 else torch.zeros((n, kd + 1), dtype=torch.float64)
+            dist.broadcast(tri, 0)
+            assert np.array_equal(tri.numpy().T, fac)
+            Xl = np.asfortranarray(B[:, q0:q1].copy())
+            assert C.pbtrs(uplo, n, kd, q1 - q0, np.asfortranarray(tri.numpy().T), kd + 1, Xl, n) == 0
+            assert np.array_equal(Xl, ref[:, q0:q1])
+        else:
+            import bandedmatrices_b200 as bm
+            from bandedmatrices_b200.sharded import ShardedCholeskySolve
+
+            tri = None
+            if rank == 0:
+                tri = torch.as_tensor(np.ascontiguousarray(ab.T)).cuda()
+                _, info = bm.pbtrf_(uplo, n, kd, tri)
+                assert info == 0
+            S = ShardedCholeskySolve(tri, uplo, n, kd, rank, world)
+            if kd <= 64:
+                assert np.array_equal(S.tri.cpu().numpy().T, fac), "broadcast Cholesky factor differs from DPBTF2"
+            Xl = bm.to_colmajor(B[:, q0:q1])
+            S.ldiv_(Xl)
+            assert np.max(np.abs(Xl.cpu().numpy() - ref[:, q0:q1])) <= 1e-12 * np.max(np.abs(ref)), ("sharded Cholesky solve", rank)
+
+
 def check_sharded_gbmm(backend, rank, world, C):
     """Column-sharded banded x banded: every rank's slab of C equals the same columns of the unsharded _gbmm! result."""
     for (n, Ab, Bb) in [(1500, (3, 2), (4, 1)), (2000, (9, 12), (10, 9)), (4096, (32, 32), (32, 32))]:
@@ -134,6 +172,7 @@ def main():
         if backend == "nccl":
             op.close()
     check_sharded_solve(backend, rank, world, C)
+    check_sharded_cholesky_solve(backend, rank, world, C)
     check_sharded_gbmm(backend, rank, world, C)
     dist.barrier()
     dist.destroy_process_group()
