@@ -583,6 +583,35 @@ __global__ void pb_reverse_rows(i64 n, i64 nrhs, double *__restrict__ b, i64 ldb
     }
 }
 
+// Non-unit triangular band solve T x = b ('N') for narrow bands through the multi-RHS back substitution of bmb200_dgbtrs (kl = 0,
+// identity pivots): 'U' directly -- DGBTRS' U sweep IS dtbsv('U','N','N') -- and 'L' as the upper-triangular solve of the
+// reversed system (same operations in the same order per entry: bit-identical to dtbsv('L','N','N')).  Used by bmb200_dtbsv.
+int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
+{
+    const size_t fbytes = up ? 0 : (size_t)n * (size_t)(k + 1) * sizeof(double), need = fbytes + (size_t)n * sizeof(i64);
+    if (need > h->backup_bytes) {
+        if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
+        BMB_CUDA(h, cudaMalloc(&h->backup, need));
+        h->backup_bytes = need;
+    }
+    double *M = (double *)h->backup;
+    i64 *idp = (i64 *)((char *)h->backup + fbytes);
+    pb_iota<<<(unsigned)imin64(cdiv64(n, 256), (i64)h->sm_count * 8), 256, 0, h->stream>>>(n, idp);
+    BMB_LAUNCH_CHECK(h);
+    if (up) return bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, dA, lda, idp, dB, ldb);
+    const unsigned gb = (unsigned)imin64(cdiv64(n * (k + 1), 256), (i64)h->sm_count * 16);
+    const unsigned gr = (unsigned)imin64(cdiv64(imax64(1, (n / 2) * nrhs), 256), (i64)h->sm_count * 16);
+    pb_reverse_factor<<<gb, 256, 0, h->stream>>>(1, n, (int)k, dA, lda, M);
+    pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
+    h->launches += 2;
+    BMB_CUDA(h, cudaGetLastError());
+    const int rc = bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, M, k + 1, idp, dB, ldb);
+    if (rc) return rc;
+    pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
+    BMB_LAUNCH_CHECK(h);
+    return 0;
+}
+
 static int pb_check(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t ldab, int &up)
 {
     if (!h) return -1;

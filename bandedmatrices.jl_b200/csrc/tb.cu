@@ -9,6 +9,7 @@
 //     descending ('L') -- the per-row order of OpenBLAS' column sweep -- into a scratch vector, then copied back.
 #include "common.cuh"
 
+int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);  // pb.cu
 int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
 
 __global__ void __launch_bounds__(256)
@@ -347,6 +348,9 @@ extern "C" int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag,
     if (!dA || !dx) return -7;
     DeviceGuard g(h->device);
     if (!(trans == 'N' || trans == 'n')) return bmb_tbsv_t_multi(h, up, unit, n, k, 1, dA, lda, dx, n > 1 ? n : 1);
+    // narrow bands, non-unit diagonal: the multi-RHS back substitution of bmb200_dgbtrs (register-window kernels, ~45 ns per
+    // column) instead of the cluster pipeline, which is built for wide bands (~250 ns per column at k = 4); pb.cu
+    if (!unit && k <= 63 && n > 1) return bmb_tri_solve_via_gbtrs(h, up, n, k, 1, dA, lda, dx, n);
     // 'U': diagonal in row k of the band array, reach k above it (mode 0 with kl = 0 divides, mode 1 does not);
     // 'L': diagonal in row 0, reach k below it (mode 2 unit, mode 3 dividing)
     const int mode = up ? (unit ? 1 : 0) : (unit ? 2 : 3);
