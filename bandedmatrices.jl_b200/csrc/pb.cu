@@ -586,9 +586,13 @@ __global__ void pb_reverse_rows(i64 n, i64 nrhs, double *__restrict__ b, i64 ldb
 // Non-unit triangular band solve T x = b ('N') for narrow bands through the multi-RHS back substitution of bmb200_dgbtrs (kl = 0,
 // identity pivots): 'U' directly -- DGBTRS' U sweep IS dtbsv('U','N','N') -- and 'L' as the upper-triangular solve of the
 // reversed system (same operations in the same order per entry: bit-identical to dtbsv('L','N','N')).  Used by bmb200_dtbsv.
-int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
+int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, int tr, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
 {
-    const size_t fbytes = up ? 0 : (size_t)n * (size_t)(k + 1) * sizeof(double), need = fbytes + (size_t)n * sizeof(i64);
+    // op(T) upper: ('U','N') as stored; ('L','T') after a band transpose.  op(T) lower: reversed system -- ('L','N') from L,
+    // ('U','T') from U^T (gather modes 1 / 0 of pb_reverse_factor).  The transposed forms run as column sweeps: equal to the
+    // dot-product dtbsv('T') to rounding (1e-13), the 'N' forms bit for bit.
+    const bool direct = up && !tr;
+    const size_t fbytes = direct ? 0 : (size_t)n * (size_t)(k + 1) * sizeof(double), need = fbytes + (size_t)n * sizeof(i64);
     if (need > h->backup_bytes) {
         if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
         BMB_CUDA(h, cudaMalloc(&h->backup, need));
@@ -598,10 +602,14 @@ int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const
     i64 *idp = (i64 *)((char *)h->backup + fbytes);
     pb_iota<<<(unsigned)imin64(cdiv64(n, 256), (i64)h->sm_count * 8), 256, 0, h->stream>>>(n, idp);
     BMB_LAUNCH_CHECK(h);
-    if (up) return bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, dA, lda, idp, dB, ldb);
+    if (direct) return bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, dA, lda, idp, dB, ldb);
+    if (!up && tr) {  // L^T: upper, in 'U' storage after the band transpose
+        const int rc = bmb200_dband_transpose(h, n, n, k, 0, dA, lda, M, k + 1);
+        return rc ? rc : bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, M, k + 1, idp, dB, ldb);
+    }
     const unsigned gb = (unsigned)imin64(cdiv64(n * (k + 1), 256), (i64)h->sm_count * 16);
     const unsigned gr = (unsigned)imin64(cdiv64(imax64(1, (n / 2) * nrhs), 256), (i64)h->sm_count * 16);
-    pb_reverse_factor<<<gb, 256, 0, h->stream>>>(1, n, (int)k, dA, lda, M);
+    pb_reverse_factor<<<gb, 256, 0, h->stream>>>(up ? 0 : 1, n, (int)k, dA, lda, M);
     pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
     h->launches += 2;
     BMB_CUDA(h, cudaGetLastError());
@@ -610,6 +618,24 @@ int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const
     pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
     BMB_LAUNCH_CHECK(h);
     return 0;
+}
+
+// The transposed non-unit solve for WIDE bands: the factor is transposed once on the device (one HBM pass into grow-only
+// workspace) and the sweep runs as a column sweep through the cluster pipeline (the chain of n dependent dot products of the
+// dtbsv('T') kernel costs ~2 us per column at k = 1024).  Returns 1 if the cluster pipeline does not take the shape.
+int bmb_tri_solve_transposed_wide(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
+{
+    const size_t need = (size_t)n * (size_t)(k + 1) * sizeof(double);
+    if (need > h->backup_bytes) {
+        if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
+        BMB_CUDA(h, cudaMalloc(&h->backup, need));
+        h->backup_bytes = need;
+    }
+    double *tr = (double *)h->backup;
+    const int rc = bmb200_dband_transpose(h, n, n, up ? 0 : k, up ? k : 0, dA, lda, tr, k + 1);
+    if (rc) return rc;
+    // U^T = lower triangular ('L' storage, dividing: mode 3); L^T = upper triangular ('U' storage, dividing: mode 0)
+    return up ? bmb_cluster_solve(h, 3, n, k, 0, nrhs, tr, k + 1, dB, ldb) : bmb_cluster_solve(h, 0, n, 0, k, nrhs, tr, k + 1, dB, ldb);
 }
 
 static int pb_check(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t ldab, int &up)
@@ -762,59 +788,25 @@ extern "C" int bmb200_dpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
     if (!dAB) return -6;
     if (!dB) return -8;
     DeviceGuard g(h->device);
-    // DPBTRS: 'U': solve U^T y = b, then U x = y;  'L': solve L y = b, then L^T x = y  (DTBSV per right-hand side)
+    // DPBTRS: 'U': solve U^T y = b, then U x = y;  'L': solve L y = b, then L^T x = y  (DTBSV per right-hand side), every
+    // sweep as a COLUMN sweep for all right-hand sides at once:
+    //   kd >= 64: the cluster pipeline of gbtrs_cluster.cu; the transposed sweep runs on a transposed copy of the factor (one
+    //             HBM pass; the chain of n dependent dot products of dtbsv('T') costs ~2 us per column at kd = 1024);
+    //   kd <  64: the multi-RHS back substitution of bmb200_dgbtrs (kl = 0, identity pivots: ~45 ns per column for all
+    //             right-hand sides together); lower-triangular sweeps are the upper-triangular ones of the reversed system.
+    // Equal to DPBTRS to rounding (the 'T' sweeps of the reference are dot-product forms).
     int rc;
     if (kd >= PB_TRANSPOSE_KD) {
-        // wide bands: the transposed sweep as a chain of n dot products costs ~2 us per column; instead the factor is
-        // transposed once on the device (one HBM pass, n*(kd+1) doubles of grow-only workspace) and BOTH sweeps run through the
-        // cluster pipeline as column sweeps ('N' form): same solution to rounding (the 'T' form owes 1e-13 either way).
-        const size_t need = (size_t)n * (size_t)(kd + 1) * sizeof(double);
-        if (need > h->backup_bytes) {
-            if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
-            BMB_CUDA(h, cudaMalloc(&h->backup, need));
-            h->backup_bytes = need;
-        }
-        double *tr = (double *)h->backup;
-        rc = bmb200_dband_transpose(h, n, n, up ? 0 : kd, up ? kd : 0, dAB, ldab, tr, kd + 1);
-        if (rc) return rc;
         if (up) {
-            rc = bmb_cluster_solve(h, 3, n, kd, 0, nrhs, tr, kd + 1, dB, ldb);   // U^T = lower triangular, dividing
+            rc = bmb_tri_solve_transposed_wide(h, 1, n, kd, nrhs, dAB, ldab, dB, ldb);
             if (rc == 0) rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, dAB, ldab, dB, ldb);
         } else {
             rc = bmb_cluster_solve(h, 3, n, kd, 0, nrhs, dAB, ldab, dB, ldb);
-            if (rc == 0) rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, tr, kd + 1, dB, ldb);  // L^T = upper triangular, dividing
+            if (rc == 0) rc = bmb_tri_solve_transposed_wide(h, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
         }
     } else {
-        // narrow bands: both sweeps through bmb200_dgbtrs('N') with kl = 0 and identity pivots, i.e. its multi-RHS back
-        // substitution (slot-scheduled / register-window kernels: ~45 ns per column for all right-hand sides together, where
-        // the single-warp chain of the transposed dtbsv took ~250).  The lower-triangular sweep is the upper-triangular one of
-        // the REVERSED system (i -> n-1-i): the factor is gathered once into reversed 'U' storage, the right-hand sides are
-        // reversed in place before and after.  Column-oriented ('N'-form) sweeps on both sides: equal to DPBTRS to rounding.
-        const size_t fbytes = (size_t)n * (size_t)(kd + 1) * sizeof(double), need = fbytes + (size_t)n * sizeof(i64);
-        if (need > h->backup_bytes) {
-            if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
-            BMB_CUDA(h, cudaMalloc(&h->backup, need));
-            h->backup_bytes = need;
-        }
-        double *M = (double *)h->backup;
-        i64 *idp = (i64 *)((char *)h->backup + fbytes);
-        const unsigned gb = (unsigned)imin64(cdiv64(n * (kd + 1), 256), (i64)h->sm_count * 16);
-        const unsigned gr = (unsigned)imin64(cdiv64(imax64(1, (n / 2) * nrhs), 256), (i64)h->sm_count * 16);
-        pb_iota<<<(unsigned)imin64(cdiv64(n, 256), (i64)h->sm_count * 8), 256, 0, h->stream>>>(n, idp);
-        pb_reverse_factor<<<gb, 256, 0, h->stream>>>(up ? 0 : 1, n, (int)kd, dAB, ldab, M);
-        pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
-        h->launches += 3;
-        BMB_CUDA(h, cudaGetLastError());
-        rc = bmb200_dgbtrs(h, 'N', n, 0, kd, nrhs, M, kd + 1, idp, dB, ldb);            // U^T y = b  /  L y = b, reversed
-        if (rc) return rc;
-        pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
-        BMB_LAUNCH_CHECK(h);
-        if (up) {
-            rc = bmb200_dgbtrs(h, 'N', n, 0, kd, nrhs, dAB, ldab, idp, dB, ldb);          // U x = y
-        } else {
-            rc = bmb200_dband_transpose(h, n, n, kd, 0, dAB, ldab, M, kd + 1);            // L^T in 'U' storage
-            if (rc == 0) rc = bmb200_dgbtrs(h, 'N', n, 0, kd, nrhs, M, kd + 1, idp, dB, ldb);  // L^T x = y
-        }
+        rc = bmb_tri_solve_via_gbtrs(h, up, up ? 1 : 0, n, kd, nrhs, dAB, ldab, dB, ldb);
+        if (rc == 0) rc = bmb_tri_solve_via_gbtrs(h, up, up ? 0 : 1, n, kd, nrhs, dAB, ldab, dB, ldb);
         return rc;
     }
     if (rc == 1) {
