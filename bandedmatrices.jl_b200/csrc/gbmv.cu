@@ -134,7 +134,7 @@ static int launch_systolic(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, double a
     const int threads = 256;
     int per_sm = 0;
     BMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gbmv_n_systolic<W, LDV>, threads, 0));
-    const SystolicPlan p = systolic_plan(m, ku, h->sm_count, per_sm, threads);
+    const SystolicPlan p = systolic_plan(m, ku, h->sm_count, per_sm, threads, h->tune.gbmv_spr);
     gbmv_n_systolic<W, LDV><<<(unsigned)p.blocks, threads, 0, h->stream>>>(m, n, (int)kl, (int)ku, alpha, dA, lda, dx,
                                                                            beta, dy, p.total_sets, p.sets_per_run,
                                                                            p.num_runs);

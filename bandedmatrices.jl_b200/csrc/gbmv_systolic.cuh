@@ -124,10 +124,16 @@ __device__ __forceinline__ void gbmv_n_systolic_body(i64 m, i64 n, int kl, int k
 struct SystolicPlan {
     i64 total_sets, sets_per_run, num_runs, blocks;
 };
-static inline SystolicPlan systolic_plan(i64 m, i64 ku, int sm_count, int blocks_per_sm, int threads)
+static inline SystolicPlan systolic_plan(i64 m, i64 ku, int sm_count, int blocks_per_sm, int threads, int spr_override = 0)
 {
     SystolicPlan p;
     p.total_sets = cdiv64(m + ku, 32);
+    if (spr_override > 0) {  // short runs, one per warp, more blocks than are resident: the hardware block scheduler balances the tail
+        p.sets_per_run = spr_override;
+        p.num_runs = cdiv64(p.total_sets, p.sets_per_run);
+        p.blocks = cdiv64(p.num_runs, threads / 32);
+        return p;
+    }
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     p.blocks = (i64)sm_count * blocks_per_sm;
     const i64 nwarps = p.blocks * (threads / 32);

@@ -6,7 +6,10 @@ import torch
 sys.path.insert(0, ".")
 import bandedmatrices_b200 as bm
 
-for lg in (27, 26, 25, 24, 23):
+spr = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+bm.handle(0).tune("gbmv_spr", spr)
+print("sets per run override:", spr)
+for lg in (27, 25, 24, 23):
     n = 1 << lg
     A = bm.brand(n, n, 4, 3, seed=1)
     x = torch.rand(n, dtype=torch.float64, device="cuda")
