@@ -247,8 +247,9 @@ __device__ __forceinline__ void pb_sts2(unsigned addr, double x, double y) { asm
 __global__ void __launch_bounds__(PB_K1T)
 pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, double *__restrict__ d_rdiag)
 {
-    __shared__ __align__(16) double xs[2][2][PB_NB];  // [buffer][x_j, x_{j+1}][column]
+    __shared__ __align__(16) double xs[2][4][PB_NB];  // the four scaled rows of a row group, [row group parity][row][column]
     __shared__ double rd[PB_NB + 1];
+    __shared__ __align__(16) double dpatch[16];        // the diagonal 4 x 4 patch of the current row group
     __shared__ int s_panel, s_fail;
     // programmatic dependent launch (the three kernels of a panel are captured with it): this grid was launched while its
     // predecessor was still running; nothing is read before the predecessor has completed and flushed, and the successor may
@@ -279,6 +280,8 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
     unsigned xs0 = (unsigned)__cvta_generic_to_shared(&xs[0][0][0]);
     unsigned rd0 = (unsigned)__cvta_generic_to_shared(&rd[0]);
     unsigned fl0 = (unsigned)__cvta_generic_to_shared(&s_fail);
+    unsigned dp0 = (unsigned)__cvta_generic_to_shared(&dpatch[0]);
+    asm volatile("mov.u32 %0, %0;" : "+r"(dp0));
     asm volatile("mov.u32 %0, %0;" : "+r"(xs0));
     asm volatile("mov.u32 %0, %0;" : "+r"(rd0));
     asm volatile("mov.u32 %0, %0;" : "+r"(fl0));
@@ -295,86 +298,103 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
         const bool inwarp = warp == ((jb * PB_LG) >> 5);  // this warp holds rows 4jb..4jb+3
         const bool rowgrp = a == jb && upper;           // this thread holds a piece of them
         const int dlane = (jb * PB_LG + jb) & 31;        // lane of the diagonal patch (a == b == jb)
-        const bool live = upper && a >= jb;
-        const bool bgt = b > jb, bge = b >= jb;         // column 4b+w against column 4jb+u: > iff bgt or (b == jb and w > u)
-        const bool isdiag = rowgrp && b == jb;
-        {   // a failure in an earlier row group stops the factorisation (one look per row group, off the per-step chain)
+        const bool bgt = b > jb;                         // this patch lies right of the diagonal patch
+        // FOUR columns (one row group) per barrier.  The 4 x 4 diagonal patch D lives in ONE thread: its ten upper entries are
+        // shuffled to every lane of the row-group warp (pipelined), every lane then factors D redundantly in registers -- four
+        // rsqrt in sequence, no further communication -- and solves its own 4 x 4 patch of the row group against it (a 4 x 4
+        // triangular substitution); the four scaled rows are posted and everyone below applies a rank-4 update.
+        const unsigned buf = (unsigned)(jb & 1) * (4u * PB_NB * 8u);  // double-buffered: the next row group posts while this one is read
+        if (inwarp) {
+            // the diagonal patch goes through shared memory (one post, broadcast loads): shuffles issued by a single warp do not
+            // pipeline (ten 64-bit shuffles cost ~300 cycles here)
+            double D[4][4];
+            if (lane == dlane) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { pb_sts2(dp0 + 32u * r, v[r][0], v[r][1]); pb_sts2(dp0 + 32u * r + 16u, v[r][2], v[r][3]); }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { pb_lds2(dp0 + 32u * r, D[r][0], D[r][1]); pb_lds2(dp0 + 32u * r + 16u, D[r][2], D[r][3]); }
+            __syncwarp();
+            double ri[4], U[4][4];
+            int bad = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!bad && 4 * jb + u < nbl && !(D[u][u] > 0.0)) bad = 4 * jb + u + 1;  // not positive definite (NaN included)
+                ri[u] = pb_rsqrt(D[u][u]);
+#pragma unroll
+                for (int c = u + 1; c < 4; ++c) U[u][c] = __dmul_rn(D[u][c], ri[u]);
+#pragma unroll
+                for (int r = u + 1; r < 4; ++r)
+#pragma unroll
+                    for (int c = r; c < 4; ++c) D[r][c] = fma(-U[u][r], U[u][c], D[r][c]);
+            }
+            if (bad && !failed) failed = bad;
+            if (rowgrp && !failed) {
+                double x[4][4];
+                if (bgt) {
+                    // a patch right of the diagonal patch: row u -= sum_{t<u} U[t][u] * x_t, then * ri[u]; every entry belongs to its row
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            double t = v[u][w];
+#pragma unroll
+                            for (int q = 0; q < u; ++q) t = fma(-U[q][u], x[q][w], t);
+                            x[u][w] = __dmul_rn(t, ri[u]);
+                            v[u][w] = x[u][w];
+                        }
+                } else {
+                    // the diagonal patch itself: its factor is the U just computed (diagonal = D * rsqrt(D) = sqrt(D)); the posted
+                    // rows carry zeros at and left of the diagonal
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            x[u][w] = (w > u) ? U[u][w] : 0.0;
+                            if (w > u) v[u][w] = U[u][w];
+                            else if (w == u) v[u][w] = __dmul_rn(D[u][u], ri[u]);
+                        }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    pb_sts2(xc_a + buf + u * (PB_NB * 8u), x[u][0], x[u][1]);
+                    pb_sts2(xc_a + buf + u * (PB_NB * 8u) + 16u, x[u][2], x[u][3]);
+                }
+            }
+            if (lane == dlane) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) asm volatile("st.shared.f64 [%0], %1;" ::"r"(rd0 + 8u * (4 * jb + u)), "d"(ri[u]) : "memory");
+                if (failed) asm volatile("st.shared.u32 [%0], %1;" ::"r"(fl0), "r"(failed) : "memory");
+            }
+        }
+        __syncthreads();
+        {
             int f;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(fl0));
             if (f) { failed = f; break; }
         }
-        // two columns per barrier: the row-group warp takes steps j and j+1 by itself (row j+1 needs x_j only inside this warp),
-        // posts both scaled rows, and everyone else applies a rank-2 update
+        // The warp that holds the NEXT row group applies the update first and alone -- its FMAs do not queue behind the other
+        // seven warps' on the FP64 pipe -- and goes straight into its pivot phase; the others start when it has issued its
+        // FMAs (named barrier 1: it arrives, they wait) and work in the shadow of its rsqrt chain.
+        const bool has_next = jb + 1 < PB_NB / 4 && 4 * (jb + 1) < nbl;   // block-uniform
+        const bool nextwarp = has_next && warp == (((jb + 1) * PB_LG) >> 5);
+        if (has_next && !nextwarp) asm volatile("bar.sync 1, %0;" ::"n"(PB_K1T) : "memory");
+        if (upper && a > jb) {
 #pragma unroll
-        for (int u = 0; u < 4; u += 2) {
-            const int j = 4 * jb + u;
-            const unsigned buf = (unsigned)((u >> 1) & 1) * (2u * PB_NB * 8u);  // two x rows per buffer
-            if (j < nbl) {  // block-uniform
-                if (inwarp) {
-                    const bool two = j + 1 < nbl;
-                    double xv0[4], xv1[4];
-                    // step j
-                    const double ajj = __shfl_sync(0xffffffffu, v[u][u], dlane);
-                    const bool ok0 = !failed && ajj > 0.0;
-                    const double rinv0 = pb_rsqrt(ajj);
-                    const double sc0 = (rowgrp && ok0) ? rinv0 : 1.0;
+            for (int u = 0; u < 4; ++u) {
+                double xr[4], xc[4];
+                pb_lds2(xr_a + buf + u * (PB_NB * 8u), xr[0], xr[1]);
+                pb_lds2(xr_a + buf + u * (PB_NB * 8u) + 16u, xr[2], xr[3]);
+                pb_lds2(xc_a + buf + u * (PB_NB * 8u), xc[0], xc[1]);
+                pb_lds2(xc_a + buf + u * (PB_NB * 8u) + 16u, xc[2], xc[3]);
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const double scaled = __dmul_rn(v[u][w], sc0);
-                        v[u][w] = scaled;
-                        xv0[w] = (rowgrp && ok0 && ((w > u) ? bge : bgt)) ? scaled : 0.0;  // 0 in the other half-warp: its rows are not touched
-                    }
-                    if (isdiag && ok0) v[u][u] = __dmul_rn(ajj, rinv0);
-                    // row j+1 of the row group -= x_j[j+1] * x_j (x_j[j+1] sits in the diagonal lane)
-                    const double xj1 = __shfl_sync(0xffffffffu, xv0[u + 1], dlane);
+                for (int uu = 0; uu < 4; ++uu)
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) v[u + 1][w] = fma(-xj1, xv0[w], v[u + 1][w]);
-                    // step j+1
-                    const double ajj1 = __shfl_sync(0xffffffffu, v[u + 1][u + 1], dlane);
-                    const bool ok1 = ok0 && two && ajj1 > 0.0;
-                    const double rinv1 = pb_rsqrt(ajj1);
-                    const double sc1 = (rowgrp && ok1) ? rinv1 : 1.0;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const double scaled = __dmul_rn(v[u + 1][w], sc1);
-                        v[u + 1][w] = scaled;
-                        xv1[w] = (rowgrp && ok1 && ((w > u + 1) ? bge : bgt)) ? scaled : 0.0;
-                    }
-                    if (isdiag && ok1) v[u + 1][u + 1] = __dmul_rn(ajj1, rinv1);
-                    if (rowgrp) {
-                        pb_sts2(xc_a + buf, xv0[0], xv0[1]);
-                        pb_sts2(xc_a + buf + 16u, xv0[2], xv0[3]);
-                        pb_sts2(xc_a + buf + PB_NB * 8u, xv1[0], xv1[1]);
-                        pb_sts2(xc_a + buf + PB_NB * 8u + 16u, xv1[2], xv1[3]);
-                    }
-                    if (!failed && !ok0) failed = j + 1;
-                    else if (!failed && two && !ok1) failed = j + 2;
-                    if (lane == dlane) {
-                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(rd0 + 8u * j), "d"(rinv0) : "memory");
-                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(rd0 + 8u * (j + 1)), "d"(rinv1) : "memory");
-                        if (failed) asm volatile("st.shared.u32 [%0], %1;" ::"r"(fl0), "r"(failed) : "memory");
-                    }
-                }
-                __syncthreads();
-                if (live) {
-                    double xr0[4], xc0[4], xr1[4], xc1[4];
-                    pb_lds2(xr_a + buf, xr0[0], xr0[1]);
-                    pb_lds2(xr_a + buf + 16u, xr0[2], xr0[3]);
-                    pb_lds2(xc_a + buf, xc0[0], xc0[1]);
-                    pb_lds2(xc_a + buf + 16u, xc0[2], xc0[3]);
-                    pb_lds2(xr_a + buf + PB_NB * 8u, xr1[0], xr1[1]);
-                    pb_lds2(xr_a + buf + PB_NB * 8u + 16u, xr1[2], xr1[3]);
-                    pb_lds2(xc_a + buf + PB_NB * 8u, xc1[0], xc1[1]);
-                    pb_lds2(xc_a + buf + PB_NB * 8u + 16u, xc1[2], xc1[3]);
-                    // inside the row group x[r] = 0 for finished rows makes them a no-op; its row j+1 already has x_j's term
-                    if (a == jb) xr0[u + 1] = 0.0;
-#pragma unroll
-                    for (int uu = 0; uu < 4; ++uu)
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) v[uu][w] = fma(-xr1[uu], xc1[w], fma(-xr0[uu], xc0[w], v[uu][w]));
-                }
+                    for (int w = 0; w < 4; ++w) v[uu][w] = fma(-xr[uu], xc[w], v[uu][w]);
             }
         }
+        if (nextwarp) asm volatile("bar.arrive 1, %0;" ::"n"(PB_K1T) : "memory");
     }
     __syncthreads();
     if (!failed) {
