@@ -93,3 +93,42 @@ def test_new_wrappers_validate_before_touching_the_device():
         bm.tbsv_("U", "N", "N", 6, 2, A.data[:, :3], x)
     with pytest.raises(TypeError):
         bm.axpy_(1.0, A, A)
+
+
+def test_cholesky_and_typed_wrappers_validate_before_touching_the_device():
+    """pbtrf_/pbtrs_ raise the reference's argument errors (src/lapack.jl:278-282, 308-314), the typed wrappers refuse element
+    types outside the four BLAS floats and mixed types, and none of them computes on CPU tensors."""
+    d = torch.zeros((6, 3), dtype=torch.float64)  # 6 columns, 3 band rows, CPU
+    with pytest.raises(ValueError):
+        bm.pbtrf_("X", 6, 2, d)               # chkuplo
+    with pytest.raises(ValueError):
+        bm.pbtrf_("U", 7, 2, d)               # Matrix must be square
+    with pytest.raises(ValueError):
+        bm.pbtrf_("U", 6, 3, d)               # Not enough bands
+    with pytest.raises(bm.DimensionMismatch):
+        bm.pbtrs_("U", 6, 2, d, torch.zeros(5, dtype=torch.float64))
+    with pytest.raises(TypeError):            # valid arguments, CPU tensors: no CPU fallback
+        bm.pbtrf_("U", 6, 2, d)
+    with pytest.raises(TypeError):
+        bm.cholesky(bm.BandedMatrix(torch.zeros((6, 3), dtype=torch.float64), 6, 1, 1))
+    h = torch.zeros((6, 3), dtype=torch.float16)
+    with pytest.raises(TypeError):            # not a BLAS float
+        bm.gbmv_("N", 6, 1, 1, 1.0, h, torch.zeros(6, dtype=torch.float16), 0.0, torch.zeros(6, dtype=torch.float16))
+    s = torch.zeros((6, 3), dtype=torch.float32)
+    with pytest.raises(TypeError):            # element types differ
+        bm.gbmv_("N", 6, 1, 1, 1.0, s, torch.zeros(6, dtype=torch.float64), 0.0, torch.zeros(6, dtype=torch.float32))
+    with pytest.raises(bm.DimensionMismatch):
+        bm.gbmv_("N", 6, 1, 1, 1.0, s, torch.zeros(5, dtype=torch.float32), 0.0, torch.zeros(6, dtype=torch.float32))
+    with pytest.raises(TypeError):            # valid arguments, CPU tensors
+        bm.gbmv_("C", 6, 1, 1, 1.0, torch.zeros((6, 3), dtype=torch.complex64), torch.zeros(6, dtype=torch.complex64), 0.0,
+                 torch.zeros(6, dtype=torch.complex64))
+    with pytest.raises(TypeError):
+        bm.gbtrf_(6, 1, 1, torch.zeros((6, 4), dtype=torch.complex128))
+
+
+def test_sharded_cholesky_solve_bounds():
+    from bandedmatrices_b200.sharded import rhs_bounds
+
+    for nrhs, world in ((7, 2), (256, 8), (3, 4)):
+        owned = [rhs_bounds(nrhs, r, world) for r in range(world)]
+        assert owned[0][0] == 0 and owned[-1][1] == nrhs and all(owned[i][1] == owned[i + 1][0] for i in range(world - 1))
