@@ -62,7 +62,7 @@ __device__ __forceinline__ double pb_rsqrt(double a)
     return y;
 }
 
-// d_state: [0] = info (0 ok, > 0 first non-positive pivot, 1-based), [1] = panel counter of the blocked path.
+// d_state: [0] = info (0 ok, > 0 first non-positive pivot, 1-based); [1] is the panel counter of the blocked path.
 // The kd+1 live columns sit in a shared-memory ring: entry U(k-d, k) at win[((k*P + d) & MASK)], P and the slot count powers of
 // two, so one add and one mask address anything relative to the current column.  A thread owns up to E entries (r, c),
 // 1 <= r <= c <= kd, of the trailing triangle RELATIVE to the current column j (offsets precomputed once, enumerated by
@@ -71,24 +71,11 @@ __device__ __forceinline__ double pb_rsqrt(double a)
 // single warp per scheduler hides nothing, so the step is kept to the instructions the dependency chain needs.
 template <int NT, int E>
 __global__ void __launch_bounds__(NT)
-pbtf2_window(i64 n_total, int kd_total, int blocked, i64 si, i64 sk, double *__restrict__ p0, int ring, int P, int *__restrict__ d_state,
-             double *__restrict__ d_rdiag, long long *__restrict__ stats)
+pbtf2_window(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p, int ring, int P, int *__restrict__ d_state, long long *__restrict__ stats)
 {
     extern __shared__ double win[];
-    __shared__ int s_panel;
-    long long tk0 = 0, tk1 = 0, tk2 = 0, acc0 = 0, acc1 = 0, acc2 = 0;  // development aid (tuning key pipe_stats)
-    if (d_state[0] != 0) return;
-    i64 j0 = 0, n = n_total;
-    int kd = kd_total;
-    if (blocked) {  // the NB x NB diagonal block of the next panel
-        if (threadIdx.x == 0) { s_panel = d_state[1] + 1; d_state[1] = s_panel; }
-        __syncthreads();
-        j0 = (i64)s_panel * PB_NB;
-        if (j0 >= n_total) return;
-        n = imin64_d(PB_NB, n_total - j0);
-        kd = kd_total < PB_NB - 1 ? kd_total : PB_NB - 1;
-    }
-    double *p = p0 + j0 * (si + sk);  // U(j0, j0)
+    long long tk0 = 0, tk1 = 0, tk2 = 0, acc0 = 0, acc1 = 0;  // development aid (tuning key pipe_stats)
+    const i64 j0 = 0;
     const int MASK = ring * P - 1, tid = threadIdx.x;
     // entry offsets relative to column j: entry (r,c) -> c*P + (c-r); its factors S(j,j+r) -> r*P + r, S(j,j+c) -> c*P + c
     int oe[E], oxr[E], oxc[E];
@@ -141,15 +128,7 @@ pbtf2_window(i64 n_total, int kd_total, int blocked, i64 si, i64 sk, double *__r
             cp_async_wait<0>();
             return;
         }
-        double dj, rinv;
-        if (blocked) {  // the blocked path owes rounding-level agreement only: one reciprocal square root instead of sqrt + divide
-            rinv = pb_rsqrt(ajj);
-            dj = __dmul_rn(ajj, rinv);
-            if (tid == 0) d_rdiag[j] = rinv;
-        } else {
-            dj = sqrt(ajj);
-            rinv = 1.0 / dj;
-        }
+        const double dj = sqrt(ajj), rinv = 1.0 / dj;  // DPBTF2: AJJ = SQRT(AJJ), then DSCAL by ONE / AJJ
         if (stats) { if (rinv == 123.456) d_state[3] = 1; tk1 = clock64(); }
 #pragma unroll
         for (int m = 0; m < E; ++m) {
@@ -165,7 +144,7 @@ pbtf2_window(i64 n_total, int kd_total, int blocked, i64 si, i64 sk, double *__r
         if (stats) { tk2 = clock64(); acc0 += tk1 - tk0; acc1 += tk2 - tk1; }
     }
     cp_async_wait<0>();
-    (void)tsi; (void)acc2;
+    (void)tsi;
     if (stats && tid == 0) {
         atomicAdd((unsigned long long *)stats + 0, (unsigned long long)acc0);
         atomicAdd((unsigned long long *)stats + 1, (unsigned long long)acc1);
@@ -708,7 +687,7 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
         while (ring < kdw + 1 + PB_PFD) ring <<= 1;
         while (P < kdw + 1) P <<= 1;  // powers of two: ring addressing is an add and a mask
         const size_t smem = (size_t)ring * P * sizeof(double);
-        typedef void (*k1_t)(i64, int, int, i64, i64, double *, int, int, int *, double *, long long *);
+        typedef void (*k1_t)(i64, int, i64, i64, double *, int, int, int *, long long *);
         // threads >= kd+1 (one row entry each) and threads * E >= kd(kd+1)/2 (the trailing triangle)
         k1_t k1;
         unsigned nt1;
@@ -718,7 +697,7 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
         else if (kdw <= 63) { k1 = pbtf2_window<256, 8>; nt1 = 256; }
         else { k1 = pbtf2_window<256, 9>; nt1 = 256; }
         BMB_CUDA(h, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1<<<1, nt1, smem, h->stream>>>(n, (int)kd, 0, si, sk, p0, ring, P, d_state, nullptr, dstats);
+        k1<<<1, nt1, smem, h->stream>>>(n, (int)kd, si, sk, p0, ring, P, d_state, dstats);
         BMB_LAUNCH_CHECK(h);
     } else {
         const i64 npanels = cdiv64(n, PB_NB);
