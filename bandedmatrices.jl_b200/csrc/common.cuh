@@ -44,7 +44,7 @@ struct bmb_tuning {
     int gbtrs_stats = 0;
     int debug = 0;
     int gbmv_spr = 0;          // > 0: systolic gbmv in short runs of this many 32-column sets, one per warp, non-persistent grid
-    int pb_nodiag = 0;         // 1: narrow-band dpbtrf never takes the one-warp register kernel; -1: it takes it for every kd <= 31 (default: kd <= 8)
+    int pb_nodiag = 0;         // -1: narrow-band dpbtrf (kd <= 31) takes the one-warp register kernel instead of the window kernel
     int pb_nopdl = 0;          // 1 captures the blocked Cholesky without programmatic dependent launch
     int sbmv_rows_k = 16;      // band width below which dsbmv uses the row kernel
 };

@@ -21,6 +21,8 @@
 //     OpenBLAS at 1e-13 * cond-ish tolerances and through ||U^T U - A||.
 // pbtrs -- DPBTRS = two DTBSV sweeps per right-hand side ('U': U^T then U; 'L': L then L^T), run for ALL right-hand sides at
 //     once (cluster pipeline of gbtrs_cluster.cu for the 'N' sweep, one chain block per right-hand side for the 'T' sweep).
+#include <type_traits>
+
 #include "common.cuh"
 
 #ifndef PB_NB
@@ -74,8 +76,6 @@ __global__ void __launch_bounds__(NT)
 pbtf2_window(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p, int ring, int P, int *__restrict__ d_state, long long *__restrict__ stats)
 {
     extern __shared__ double win[];
-    long long tk0 = 0, tk1 = 0, tk2 = 0, acc0 = 0, acc1 = 0;  // development aid (tuning key pipe_stats)
-    const i64 j0 = 0;
     const int MASK = ring * P - 1, tid = threadIdx.x;
     // entry offsets relative to column j: entry (r,c) -> c*P + (c-r); its factors S(j,j+r) -> r*P + r, S(j,j+c) -> c*P + c
     int oe[E], oxr[E], oxc[E];
@@ -91,65 +91,73 @@ pbtf2_window(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p, int ring, in
     }
     const i64 diag = si + sk;
     const i64 tsk = (i64)tid * sk, tsi = (i64)tid * si;
-    auto fetch = [&](i64 k) {          // column k of the block -> its ring slot
-        if (k < n) {
-            const int dmax = k < kd ? (int)k : kd;
-            const int base = (int)((k * P) & MASK);
-            const double *src = p + k * diag;
-            for (int d = tid; d <= dmax; d += NT) cp_async8(win + ((base + d) & MASK), src - (i64)d * si);
-        }
+    // column k of the band -> its ring slot; NT >= kd+1, so one copy per thread.  The running column advances by one per step:
+    // pointer and ring offset are stepped, not recomputed (this runs inside the per-column chain of a single small CTA)
+    i64 fk = 0;
+    const double *fsrc = p - tsi;      // &U(k - tid, k) for k = 0
+    int fbase = tid;                   // (k*P + tid) & MASK
+    auto fetch_next = [&]() {
+        if (fk < n && tid <= (fk < kd ? (int)fk : kd)) cp_async8(win + fbase, fsrc);
         cp_async_commit();
+        ++fk;
+        fsrc += diag;
+        fbase = (fbase + P) & MASK;
     };
-    for (i64 k = 0; k < kd + PB_PFD; ++k) fetch(k);
+    for (int k = 0; k < kd + PB_PFD; ++k) fetch_next();
     cp_async_wait<0>();
     __syncthreads();
     int jP = 0;
-    double *rowp = p;  // U(j, j)
-    for (i64 j = 0; j < n; ++j, jP = (jP + P) & MASK, rowp += diag) {
-        if (stats) tk0 = clock64();
-        const int kn = (int)imin64_d(kd, n - 1 - j);
+    double *rowp = p + tsk;  // &U(j, j + tid)
+    // one column step; FULL: the whole kd x kd trailing triangle is inside the matrix (all but the last kd columns), so which
+    // entries a thread owns is a per-thread constant and nothing about the step depends on j
+    bool mine[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) mine[m] = tid + m * NT < kd * (kd + 1) / 2;
+    auto step = [&](auto full_tag, i64 j) -> bool {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int kn = FULL ? kd : (int)imin64_d(kd, n - 1 - j);
         const int cnt = kn * (kn + 1) / 2;
         // everything that does not depend on the pivot is loaded first
         const double ajj = win[jP];
         double ev[E], xr[E], xc[E];
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-            const bool ok = tid + m * NT < cnt;
+            const bool ok = FULL ? mine[m] : (tid + m * NT < cnt);
             ev[m] = ok ? win[(oe[m] + jP) & MASK] : 0.0;
             xr[m] = ok ? win[(oxr[m] + jP) & MASK] : 0.0;
             xc[m] = ok ? win[(oxc[m] + jP) & MASK] : 0.0;
         }
-        double rowv = 0.0;
-        if (NT > 64 || tid <= kn) rowv = (tid <= kn) ? win[(tid * P + tid + jP) & MASK] : 0.0;
+        const double rowv = (tid <= kn) ? win[(tid * P + tid + jP) & MASK] : 0.0;
         if (ajj <= 0.0) {  // not positive definite: DPBTF2 stops here with info = j+1 and the trailing window as updated so far
             for (int c = 0; c <= kn; ++c)
                 for (int d = tid; d <= c; d += NT) p[(j + c - d) * si + (j + c) * sk] = win[(int)(((j + c) * P + d) & MASK)];
-            if (tid == 0) d_state[0] = (int)(j0 + j + 1);
+            if (tid == 0) d_state[0] = (int)(j + 1);
             cp_async_wait<0>();
-            return;
+            return false;
         }
         const double dj = sqrt(ajj), rinv = 1.0 / dj;  // DPBTF2: AJJ = SQRT(AJJ), then DSCAL by ONE / AJJ
-        if (stats) { if (rinv == 123.456) d_state[3] = 1; tk1 = clock64(); }
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-            if (tid + m * NT < cnt) {
+            if (FULL ? mine[m] : (tid + m * NT < cnt)) {
                 const double t = -__dmul_rn(xc[m], rinv);
                 if (t != 0.0) win[(oe[m] + jP) & MASK] = fma(t, __dmul_rn(xr[m], rinv), ev[m]);  // OpenBLAS dsyr skips zero entries of x
             }
         }
-        if (tid <= kn) rowp[tsk] = tid == 0 ? dj : __dmul_rn(rowv, rinv);  // row j is final: U(j, j+tid)
-        fetch(j + kd + PB_PFD);
+        if (tid <= kn) *rowp = tid == 0 ? dj : __dmul_rn(rowv, rinv);  // row j is final: U(j, j+tid)
+        fetch_next();
         cp_async_wait<PB_PFD - 1>();
         __syncthreads();
-        if (stats) { tk2 = clock64(); acc0 += tk1 - tk0; acc1 += tk2 - tk1; }
-    }
+        jP = (jP + P) & MASK;
+        rowp += diag;
+        return true;
+    };
+    i64 j = 0;
+    for (; j + kd < n; ++j)
+        if (!step(std::true_type{}, j)) return;
+    for (; j < n; ++j)
+        if (!step(std::false_type{}, j)) return;
     cp_async_wait<0>();
-    (void)tsi;
-    if (stats && tid == 0) {
-        atomicAdd((unsigned long long *)stats + 0, (unsigned long long)acc0);
-        atomicAdd((unsigned long long *)stats + 1, (unsigned long long)acc1);
-        atomicAdd((unsigned long long *)stats + 4, (unsigned long long)n);
-    }
+    (void)stats;
 }
 
 // ---- kd <= 31: DPBTF2 on ONE warp, register resident, no shared memory and no barrier.  Lane d owns diagonal d: it holds
@@ -158,7 +166,8 @@ pbtf2_window(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p, int ring, in
 // lane 0's entry of row j (one shuffle), every lane takes sqrt and reciprocal itself, x_d = S(j,j+d)/sqrt is ALREADY in lane d;
 // entry S(j+r, j+r+d) -= x_{r+d} x_r needs one broadcast (x_r) and one shift (x_{r+d}) per r.  Per column the dependency chain is
 // shuffle + sqrt + divide + multiply + one shared-memory post + FMA; in practice the single warp is bound by its instruction
-// count (~700 cycles per column at kd = 4, ~40 more per extra diagonal), so dispatch uses it for kd <= 8 only.  The
+// count (~700 cycles per column at kd = 4, ~40 more per extra diagonal) and the trimmed window kernel is faster at every kd, so
+// dispatch does not use it (tuning key pb_nodiag = -1 selects it; the tests do).  The
 // order per entry is DPBTF2's (ascending j, t = -x_c rounded, zero x_c skipped): factors stay bit-identical to OpenBLAS.  After
 // a non-positive pivot the warp goes `dead`: x = 0 (no update does anything), rows are written back as they stand.
 template <int KD>
@@ -666,16 +675,11 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
     const int init[2] = {0, -1};
     BMB_CUDA(h, cudaMemcpyAsync(d_state, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     const bool blocked = kd > 64;
-    long long *dstats = nullptr;
-    if (h->tune.pipe_stats && !blocked) {
-        if (bmb_ensure_scratch(h, 4096) != 0) return BMB200_ERR_CUDA;
-        dstats = (long long *)((char *)h->scratch + 2048);
-        BMB_CUDA(h, cudaMemsetAsync(dstats, 0, 8 * sizeof(long long), h->stream));
-    }
-    // measured (n = 2^20, ns per column, one-warp kernel / window kernel): kd = 4: 358 / 437, 8: 548 / ~600, 16: 610 / 562,
-    // 31: 1222 / ~750 -- a single warp pays ~40 cycles per extra diagonal, so it only takes the narrowest bands
-    const bool force_diag = h->tune.pb_nodiag == -1 && kd <= 31;
-    if (!blocked && (kd <= 8 || force_diag) && h->tune.pb_nodiag != 1) {
+    long long *dstats = nullptr;  // (the cycle breakdown that guided the window kernel was removed with its clock reads)
+    // measured (n = 2^19, ns per column, one-warp register kernel / window kernel after its per-step instruction count was cut):
+    // kd = 2: 318 / 254, 4: 343 / 254, 8: 463 / 276, 16: 610 / 358, 31: 1222 / 484 -- the window kernel takes every kd <= 64; the
+    // one-warp kernel stays reachable through the tuning block (pb_nodiag = -1) and is tested on every kd <= 31
+    if (!blocked && kd <= 31 && h->tune.pb_nodiag == -1) {
         if (kd <= 4) pbtf2_diag<4><<<1, 32, 0, h->stream>>>(n, (int)kd, si, sk, p0, d_state);
         else if (kd <= 8) pbtf2_diag<8><<<1, 32, 0, h->stream>>>(n, (int)kd, si, sk, p0, d_state);
         else if (kd <= 16) pbtf2_diag<16><<<1, 32, 0, h->stream>>>(n, (int)kd, si, sk, p0, d_state);
@@ -691,11 +695,15 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
         // threads >= kd+1 (one row entry each) and threads * E >= kd(kd+1)/2 (the trailing triangle)
         k1_t k1;
         unsigned nt1;
-        if (kdw <= 7) { k1 = pbtf2_window<32, 1>; nt1 = 32; }
-        else if (kdw <= 15) { k1 = pbtf2_window<64, 2>; nt1 = 64; }
-        else if (kdw <= 31) { k1 = pbtf2_window<128, 4>; nt1 = 128; }
-        else if (kdw <= 63) { k1 = pbtf2_window<256, 8>; nt1 = 256; }
-        else { k1 = pbtf2_window<256, 9>; nt1 = 256; }
+        // the fewest entry slots E per thread for the thread count (every slot costs instructions on the per-column chain)
+        if (kdw <= 7) { k1 = pbtf2_window<32, 1>; nt1 = 32; }          // T = kd(kd+1)/2 <= 28
+        else if (kdw <= 10) { k1 = pbtf2_window<32, 2>; nt1 = 32; }    // <= 55
+        else if (kdw <= 15) { k1 = pbtf2_window<64, 2>; nt1 = 64; }    // <= 120
+        else if (kdw <= 22) { k1 = pbtf2_window<128, 2>; nt1 = 128; }  // <= 253
+        else if (kdw <= 31) { k1 = pbtf2_window<128, 4>; nt1 = 128; }  // <= 496
+        else if (kdw <= 44) { k1 = pbtf2_window<256, 4>; nt1 = 256; }  // <= 990
+        else if (kdw <= 63) { k1 = pbtf2_window<256, 8>; nt1 = 256; }  // <= 2016
+        else { k1 = pbtf2_window<256, 9>; nt1 = 256; }                 // 2080
         BMB_CUDA(h, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k1<<<1, nt1, smem, h->stream>>>(n, (int)kd, si, sk, p0, ring, P, d_state, dstats);
         BMB_LAUNCH_CHECK(h);
@@ -764,12 +772,6 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
     int st[2];
     BMB_CUDA(h, cudaMemcpyAsync(st, d_state, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
     BMB_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (dstats) {
-        long long hs[7];
-        BMB_CUDA(h, cudaMemcpy(hs, dstats, sizeof(hs), cudaMemcpyDeviceToHost));
-        const double c = hs[4] ? (double)hs[4] : 1.0;
-        if (!blocked) fprintf(stderr, "[bmb200] pbtf2_window cycles per column (thread 0): loads + pivot %0.f | update, row store, fetch, barrier %.0f\n", hs[0] / c, hs[1] / c);
-    }
     *info = st[0];
     return 0;
 }
