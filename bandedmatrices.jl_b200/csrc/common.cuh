@@ -43,6 +43,7 @@ struct bmb_tuning {
     int gbtrs_pfdist = 6;      // L2 prefetch distance (panels) of the cluster solve
     int gbtrs_stats = 0;
     int debug = 0;
+    int typed_nowin = 0;       // 1 sends the S/C/Z band LU to the global-memory kernel even when the shared-memory window fits
     int gbmv_spr = 0;          // > 0: systolic gbmv in short runs of this many 32-column sets, one per warp, non-persistent grid
     int pb_nodiag = 0;         // -1: narrow-band dpbtrf (kd <= 31) takes the one-warp register kernel instead of the window kernel
     int pb_nopdl = 0;          // 1 captures the blocked Cholesky without programmatic dependent launch

@@ -259,6 +259,132 @@ tgbtf2(i64 m, i64 n, i64 kl, i64 ku, T *__restrict__ ab, i64 ldab, i64 *__restri
     if (tid == 0) d_info[0] = info;
 }
 
+// ---- gbtf2 for narrow bands: the kv+1 live columns of the LU storage sit in a shared-memory ring (whole columns of
+// RP = 2kl+ku+1 entries, fill-in rows zeroed on entry as xGBTF2 does), so a step touches global memory only to retire column j and
+// to fetch column j+kv+PF.  Three barriers per step: pivot search (warp 0) | every thread computes the NEW value of its entries
+// of the (km+1) x (ju-j+1) block from OLD values only (row interchange, reciprocal scaling and rank-1 update fused: l_t and u_c are
+// recomputed per entry) | write.  Same operation order per entry as the global-memory kernel above.
+#define TW_PF 4
+template <typename T, int NT, int E>
+__global__ void __launch_bounds__(NT)
+tgbtf2_win(i64 m, i64 n, int kl, int ku, T *__restrict__ ab, i64 ldab, i64 *__restrict__ ipiv, int *__restrict__ d_info, int slots, int RP)
+{
+    typedef Num<T> N;
+    typedef typename N::real R;
+    extern __shared__ __align__(16) unsigned char tw_raw[];
+    T *win = reinterpret_cast<T *>(tw_raw);
+    __shared__ int s_jp;
+    __shared__ T s_piv;
+    const int kv = kl + ku, tid = threadIdx.x, lane = tid & 31, SM = slots - 1;
+    const i64 mn = m < n ? m : n;
+    auto colp = [&](i64 c) { return win + (size_t)((int)c & SM) * RP; };
+    // column c of the LU storage -> its slot, ASYNCHRONOUSLY (a plain load + shared store would put one global-memory latency on
+    // every step of the chain); fill-in rows (b < kl) and rows outside the matrix start as zeros.  One commit group per call.
+    auto fetch = [&](i64 c) {
+        if (c < n) {
+            T *dst = colp(c);
+            for (int b = tid; b < RP; b += NT) {
+                const i64 i = c - kv + b;  // matrix row of band row b
+                const bool ok = b >= kl && i >= 0 && i < m;
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + b);
+                const int sz = ok ? (int)sizeof(T) : 0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(sa), "l"(ab + (ok ? b + c * ldab : 0)), "n"(sizeof(T)), "r"(sz) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (i64 c = 0; c < kv + 1 + TW_PF; ++c) fetch(c);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    i64 ju = 0;
+    int info = 0;
+    for (i64 j = 0; j < mn; ++j) {
+        const int km = (int)(kl < m - 1 - j ? kl : m - 1 - j);
+        T *cj = colp(j) + kv;  // cj[t] = A[j+t, j]
+        if (tid < 32) {
+            R best = (R)-1;
+            int bidx = 0;
+            for (int t = lane; t <= km; t += 32) {
+                const R v = N::abs1(cj[t]);
+                if (v > best) { best = v; bidx = t; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const R ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+            }
+            if (lane == 0) {
+                if (!(best >= (R)0) || bidx > km) bidx = 0;  // all-NaN column: IxAMAX returns the first index
+                s_jp = bidx;
+                s_piv = cj[bidx];
+                ipiv[j] = j + bidx + 1;
+            }
+        }
+        __syncthreads();
+        const int jp = s_jp;
+        const T piv = s_piv;
+        const bool nz = !N::iszero(piv);
+        if (nz) {
+            const i64 jun = j + ku + jp < n - 1 ? j + ku + jp : n - 1;
+            if (jun > ju) ju = jun;
+        } else if (info == 0) info = (int)(j + 1);
+        const int ncol = nz ? (int)(ju - j) + 1 : 0, total = (km + 1) * ncol;
+        const T rinv = nz ? N::recip(piv) : N::zero();
+        T nv[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int e = tid + q * NT;
+            if (e < total) {
+                const int cc = e / (km + 1), t = e - cc * (km + 1);   // column j+cc, row j+t
+                const T *pc = colp(j + cc) + (kv - cc);               // pc[t] = A[j+t, j+cc]
+                const int ts = t == 0 ? jp : (t == jp ? 0 : t);       // row interchange j <-> j+jp
+                const T v = pc[ts];
+                if (cc == 0) nv[q] = t == 0 ? v : N::mul(v, rinv);
+                else if (t == 0) nv[q] = v;
+                else {
+                    const T lt = N::mul(cj[ts], rinv), uc = pc[jp];
+                    nv[q] = N::fma(N::neg(lt), uc, v);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int e = tid + q * NT;
+            if (e < total) {
+                const int cc = e / (km + 1), t = e - cc * (km + 1);
+                colp(j + cc)[kv - cc + t] = nv[q];
+            }
+        }
+        __syncthreads();
+        // column j is final: retire it (in-matrix rows only), then its slot takes column j + kv + 1 + PF
+        {
+            const T *src = colp(j);
+            for (int b = tid; b < RP; b += NT) {
+                const i64 i = j - kv + b;
+                if (i >= 0 && i < m) ab[b + j * ldab] = src[b];
+            }
+        }
+        __syncthreads();
+        fetch(j + kv + 1 + TW_PF);
+        // the column fetched TW_PF steps ago is complete before anybody can touch it (first use: TW_PF + 1 steps after its fetch);
+        // the barriers of the next step publish it
+        asm volatile("cp.async.wait_group %0;" ::"n"(TW_PF - 1) : "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // columns mn .. n-1 of a wide matrix and whatever is still in the ring
+    for (i64 c = mn; c < n && c <= mn + kv + TW_PF; ++c) {
+        const T *src = colp(c);
+        for (int b = tid; b < RP; b += NT) {
+            const i64 i = c - kv + b;
+            if (i >= 0 && i < m) ab[b + c * ldab] = src[b];
+        }
+    }
+    if (tid == 0) d_info[0] = info;
+}
+
 // ---- gbtrs: one CTA per right-hand side; op = 0 'N', 1 'T', 2 'C' -----------------------------------------------------------
 // The right-hand side lives in global memory (L2); every sweep step is: the owner of x[j] finishes it, a barrier, everyone
 // subtracts its multiple from the entries in reach.  (A correctness-first kernel: the tuned pipelines exist for Float64 only.)
@@ -602,8 +728,27 @@ int gbtrf_impl(bmb200_ctx *h, i64 m, i64 n, i64 kl, i64 ku, void *dAB, i64 ldab,
     DeviceGuard g(h->device);
     int *d_info = h->d_info + 28;
     const i64 work = (kl + 1) * (kl + ku + 1);
-    const unsigned nt = work <= 64 ? 64 : (work <= 1024 ? 256 : 1024);
-    tgbtf2<T><<<1, nt, 0, h->stream>>>(m, n, kl, ku, (T *)dAB, ldab, d_ipiv, d_info);
+    // narrow bands: the shared-memory window kernel (the live columns never leave the SM); otherwise the global-memory kernel
+    int slots = 8;
+    while (slots < kl + ku + 1 + TW_PF + 1) slots <<= 1;
+    const int RP = (int)(2 * kl + ku + 1);
+    const size_t smem = (size_t)slots * RP * sizeof(T);
+    // (measured, n = 10^5 / 2*10^4, ns per column, window / global: (4,3) 1078 / 1308, (32,32) 2802 / 2277: the window kernel pays
+    // for its per-entry index arithmetic once a thread owns several entries, so it only takes the narrowest bands)
+    if (work <= 256 && smem <= 200 * 1024 && !h->tune.typed_nowin) {
+        auto launch = [&](auto kern, unsigned nt) -> int {
+            BMB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<1, nt, smem, h->stream>>>(m, n, (int)kl, (int)ku, (T *)dAB, ldab, d_ipiv, d_info, slots, RP);
+            return 0;
+        };
+        int rc;
+        if (work <= 64) rc = launch(tgbtf2_win<T, 64, 1>, 64);
+        else rc = launch(tgbtf2_win<T, 128, 2>, 128);
+        if (rc) return rc;
+    } else {
+        const unsigned nt = work <= 64 ? 64 : (work <= 1024 ? 256 : 1024);
+        tgbtf2<T><<<1, nt, 0, h->stream>>>(m, n, kl, ku, (T *)dAB, ldab, d_ipiv, d_info);
+    }
     BMB_LAUNCH_CHECK(h);
     BMB_CUDA(h, cudaMemcpyAsync(info, d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     BMB_CUDA(h, cudaStreamSynchronize(h->stream));

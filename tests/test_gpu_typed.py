@@ -78,6 +78,16 @@ def test_typed_hbmv(bm, oracle_ob, rng, dt, shape):
 @pytest.mark.parametrize("shape", [(1, 1, 0, 0), (12, 12, 2, 1), (300, 300, 4, 3), (250, 250, 1, 6), (400, 400, 16, 16), (120, 120, 40, 33),
                                    (60, 60, 70, 80), (3000, 3000, 2, 2)])
 def test_typed_lu_and_solve(bm, oracle_ob, rng, dt, shape):
+    """Both LU kernels (shared-memory window for the narrowest bands, global-memory otherwise; tuning key typed_nowin forces the latter)."""
+    for nowin in (0, 1):
+        bm.handle(0).tune("typed_nowin", nowin)
+        try:
+            _typed_lu_case(bm, oracle_ob, rng, dt, shape)
+        finally:
+            bm.handle(0).tune("reset", 0)
+
+
+def _typed_lu_case(bm, oracle_ob, rng, dt, shape):
     m, n, kl, ku = shape
     ldab = 2 * kl + ku + 1
     ab = _rand(rng, (ldab, n), dt)
