@@ -149,7 +149,9 @@ def test_wide_band_blocked_path_bit_identical_to_dgbtf2(bm, oracle_c, rng, shape
 
 @pytest.mark.parametrize("shape", [(2600, 300, 200, 3), (5000, 1024, 1024, 2), (1800, 150, 140, 1), (4100, 129, 500, 2),
                                    (3001, 333, 217, 2), (1000, 500, 300, 1), (2000, 0, 400, 2), (2500, 400, 0, 2),
-                                   (777, 130, 129, 1), (20011, 160, 150, 19)])
+                                   (777, 130, 129, 1), (20011, 160, 150, 19),
+                                   # mid-width interchange-free bands: beyond the register-window solves, now also on the cluster pipeline
+                                   (3000, 100, 100, 4), (2500, 70, 90, 16), (1500, 128, 128, 2), (2200, 64, 10, 3), (1900, 20, 120, 5)])
 def test_wide_band_dominant_optimistic_lu_and_blocked_solve(bm, oracle_c, rng, shape):
     """Diagonally dominant wide bands (the C5 regime): the pipelined factorisation takes its optimistic path
     (diagonal pivots, verified), the solve the panel-blocked interchange-free kernel.  Pivots = 1:n, factors and
