@@ -200,16 +200,19 @@ gbtrs_n_kernel(i64 n, int kl, int ku, i64 nrhs, const double *__restrict__ ab, i
 // 'T' / 'C' (real): solve A^T X = B.  U^T forward substitution then L^T backward sweep with the
 // inverse row interchanges.  Dot-product form (reference DTBSV-T / DGEMV-T); one warp per RHS column,
 // operands straight from global/L2.  Not on a benchmark path: kept simple.
+int bmb_gbtrs_t_fast(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb, int *u_done,
+                     int *l_done);  // pb.cu
+
 __global__ void __launch_bounds__(128)
 gbtrs_t_kernel(i64 n, int kl, int ku, i64 nrhs, const double *__restrict__ ab, i64 ldab,
-               const i64 *__restrict__ ipiv, double *__restrict__ b, i64 ldb)
+               const i64 *__restrict__ ipiv, double *__restrict__ b, i64 ldb, int skip_u)
 {
     const int lane = threadIdx.x & 31;
     const i64 c = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= nrhs) return;
     const int kv = kl + ku;
     double *x = b + c * ldb;
-    for (i64 j = 0; j < n; ++j) {  // U^T y = b
+    for (i64 j = skip_u ? n : 0; j < n; ++j) {  // U^T y = b
         double part = 0.0;
         const i64 i0 = (j - kv > 0) ? j - kv : 0;
         for (i64 i = i0 + lane; i < j; i += 32) part = fma(ab[(kv + i - j) + j * ldab], x[i], part);
@@ -402,8 +405,14 @@ extern "C" int bmb200_dgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t k
     if (!dAB || !d_ipiv || !dB) return -7;
     DeviceGuard g(h->device);
     if (tr) {
+        // the U^T half (and, for interchange-free factors, the L^T half) as column sweeps through the tuned 'N' machinery (pb.cu);
+        // what is left -- the L^T half of a factorisation with interchanges -- runs the generic one-warp-per-RHS kernel below
+        int u_done = 0, l_done = 0;
+        const int rcf = bmb_gbtrs_t_fast(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb, &u_done, &l_done);
+        if (rcf) return rcf;
+        if (u_done && l_done) return 0;
         const i64 blocks = cdiv64(nrhs, 4);
-        gbtrs_t_kernel<<<(unsigned)blocks, 128, 0, h->stream>>>(n, (int)kl, (int)ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+        gbtrs_t_kernel<<<(unsigned)blocks, 128, 0, h->stream>>>(n, (int)kl, (int)ku, nrhs, dAB, ldab, d_ipiv, dB, ldb, u_done);
         BMB_LAUNCH_CHECK(h);
         return 0;
     }

@@ -257,16 +257,24 @@ static int launch_noswap(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const d
 int bmb_gbtrs_cluster(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
 
 // returns 1 when not applicable (the caller then runs the general kernel), 0 on success, <0 on error
-int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb)
+// number of rows j with ipiv[j] != j+1 (synchronises); < 0: CUDA error code
+int bmb_count_interchanges(bmb200_ctx *h, i64 n, const i64 *d_ipiv, int *count)
 {
-    if (h->tune.gbtrs_noblock) return 1;
     int *cnt = h->d_info + 16;
     BMB_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int), h->stream));
     gbtrs_count_interchanges<<<h->sm_count, 256, 0, h->stream>>>(n, d_ipiv, cnt);
     BMB_LAUNCH_CHECK(h);
-    int hc = 0;
-    BMB_CUDA(h, cudaMemcpyAsync(&hc, cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    BMB_CUDA(h, cudaMemcpyAsync(count, cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     BMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb)
+{
+    if (h->tune.gbtrs_noblock) return 1;
+    int hc = 0;
+    const int rcc = bmb_count_interchanges(h, n, d_ipiv, &hc);
+    if (rcc) return rcc;
     if (hc != 0) return 1;
     {   // one cluster per right-hand side, pipelined through distributed shared memory (gbtrs_cluster.cu)
         const int rc = bmb_gbtrs_cluster(h, n, kl, ku, nrhs, dAB, ldab, dB, ldb);

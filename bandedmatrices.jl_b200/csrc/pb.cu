@@ -646,6 +646,65 @@ int bmb_tri_solve_transposed_wide(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs,
     return up ? bmb_cluster_solve(h, 3, n, k, 0, nrhs, tr, k + 1, dB, ldb) : bmb_cluster_solve(h, 0, n, 0, k, nrhs, tr, k + 1, dB, ldb);
 }
 
+// ---- ldiv!(transpose(F), B) (src/banded/linalg.jl:41-47 -> dgbtrs_('T')): U^T y = b, then L^T x = y with the interchanges undone.
+// The U^T sweep never involves the pivots: it always runs as a column sweep on a reversed / transposed copy of U (helpers
+// above).  For interchange-free factors L^T is a unit upper-triangular band: gathered once into 'U' storage with an explicit unit
+// diagonal and solved the same way (dividing by 1 is exact).  *u_done / *l_done tell the caller (gbtrs.cu) which halves are left
+// for its generic kernel. ----
+__global__ void __launch_bounds__(256)
+pb_gather_lt(i64 n, int kl, int kv, const double *__restrict__ ab, i64 ldab, double *__restrict__ dst)
+{
+    const i64 total = n * (kl + 1);
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 j = e / (kl + 1);
+        const int b = (int)(e - j * (kl + 1));  // 'U' storage of L^T: band row b holds (L^T)[j-(kl-b), j] = L[j, j-(kl-b)]
+        const i64 i = j - (kl - b);
+        double v = 0.0;
+        if (b == kl) v = 1.0;
+        else if (i >= 0) v = ab[(kv + (kl - b)) + i * ldab];
+        dst[e] = v;
+    }
+}
+int bmb_count_interchanges(bmb200_ctx *h, i64 n, const i64 *d_ipiv, int *count);  // gbtrs_blocked.cu
+
+int bmb_gbtrs_t_fast(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb, int *u_done,
+                     int *l_done)
+{
+    *u_done = *l_done = 0;
+    if (n < 2) return 0;
+    const i64 kv = kl + ku;
+    int rc = (kv <= 63) ? bmb_tri_solve_via_gbtrs(h, 1, 1, n, kv, nrhs, dAB, ldab, dB, ldb) : bmb_tri_solve_transposed_wide(h, 1, n, kv, nrhs, dAB, ldab, dB, ldb);
+    if (rc == 1) return 0;  // the cluster pipeline does not take this shape: everything is left to the caller
+    if (rc) return rc;
+    *u_done = 1;
+    if (kl == 0) { *l_done = 1; return 0; }
+    int hc = 0;
+    rc = bmb_count_interchanges(h, n, d_ipiv, &hc);
+    if (rc) return rc;
+    if (hc != 0) return 0;  // interchanges: the L^T half stays with the caller's kernel
+    const size_t fbytes = (size_t)n * (size_t)(kl + 1) * sizeof(double), need = fbytes + (size_t)n * sizeof(i64);
+    if (need > h->backup_bytes) {
+        if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
+        BMB_CUDA(h, cudaMalloc(&h->backup, need));
+        h->backup_bytes = need;
+    }
+    double *M = (double *)h->backup;
+    i64 *idp = (i64 *)((char *)h->backup + fbytes);
+    pb_gather_lt<<<(unsigned)imin64(cdiv64(n * (kl + 1), 256), (i64)h->sm_count * 16), 256, 0, h->stream>>>(n, (int)kl, (int)kv, dAB, ldab, M);
+    BMB_LAUNCH_CHECK(h);
+    if (kl <= 63) {
+        pb_iota<<<(unsigned)imin64(cdiv64(n, 256), (i64)h->sm_count * 8), 256, 0, h->stream>>>(n, idp);
+        BMB_LAUNCH_CHECK(h);
+        rc = bmb200_dgbtrs(h, 'N', n, 0, kl, nrhs, M, kl + 1, idp, dB, ldb);
+    } else {
+        rc = bmb_cluster_solve(h, 0, n, 0, kl, nrhs, M, kl + 1, dB, ldb);
+        if (rc == 1) return 0;
+    }
+    if (rc) return rc;
+    *l_done = 1;
+    return 0;
+}
+
 static int pb_check(bmb200_handle_t h, char uplo, int64_t n, int64_t kd, int64_t ldab, int &up)
 {
     if (!h) return -1;
