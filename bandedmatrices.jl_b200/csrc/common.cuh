@@ -38,6 +38,7 @@ struct bmb_tuning {
     int pipe_stats = 0;        // 1 prints the chain CTA's cycle breakdown
     int gbtrs_noblock = 0;     // 1 disables the panel-blocked interchange-free solve
     int gbtrs_pfdist_blocked = 1;
+    int gbtrs_nosplit = 0;     // 1: factors with interchanges keep both sweeps on the generic kernels (no cluster U sweep)
     int gbtrs_nocluster = 0;   // 1 disables the cluster solve
     int gbtrs_cluster = 0;     // > 0 forces the cluster size
     int gbtrs_pfdist = 6;      // L2 prefetch distance (panels) of the cluster solve

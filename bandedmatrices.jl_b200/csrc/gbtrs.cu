@@ -22,7 +22,7 @@ int bmb_gbtrs_blocked(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doub
 template <int NR, int KPL, int SB>
 __global__ void __launch_bounds__(GBTRS_WARPS * 32)
 gbtrs_n_kernel(i64 n, int kl, int ku, i64 nrhs, const double *__restrict__ ab, i64 ldab,
-               const i64 *__restrict__ ipiv, double *__restrict__ b, i64 ldb, int ring)
+               const i64 *__restrict__ ipiv, double *__restrict__ b, i64 ldb, int ring, int skip_u)
 {
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -111,7 +111,7 @@ gbtrs_n_kernel(i64 n, int kl, int ku, i64 nrhs, const double *__restrict__ ab, i
     }
 
     // ---------------- backward: U x = y (DTBSV upper, no-trans, non-unit; bandwidth kv) ----------------
-    {
+    if (!skip_u) {
         // rows [lo, n) resident
         i64 lo = (n - (kv + 64) > 0) ? n - (kv + 64) : 0;
         for (int q = 0; q < nq; ++q)
@@ -200,6 +200,7 @@ gbtrs_n_kernel(i64 n, int kl, int ku, i64 nrhs, const double *__restrict__ ab, i
 // 'T' / 'C' (real): solve A^T X = B.  U^T forward substitution then L^T backward sweep with the
 // inverse row interchanges.  Dot-product form (reference DTBSV-T / DGEMV-T); one warp per RHS column,
 // operands straight from global/L2.  Not on a benchmark path: kept simple.
+int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
 int bmb_gbtrs_t_fast(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv, double *dB, i64 ldb, int *u_done,
                      int *l_done);  // pb.cu
 
@@ -249,7 +250,7 @@ gbtrs_t_kernel(i64 n, int kl, int ku, i64 nrhs, const double *__restrict__ ab, i
 template <int KPL, int KPU>
 __global__ void __launch_bounds__(GW_THREADS, 1)
 gbtrs_wide_kernel(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab, const i64 *__restrict__ ipiv,
-                  double *__restrict__ b, i64 ldb, int ring)
+                  double *__restrict__ b, i64 ldb, int ring, int skip_u)
 {
     extern __shared__ double rg[];
     const int tid = threadIdx.x, M = ring - 1;
@@ -302,7 +303,7 @@ gbtrs_wide_kernel(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
         for (i64 r = done + tid; r < n; r += GW_THREADS) x[r] = RGW(r);
         __syncthreads();
     }
-    {
+    if (!skip_u) {
         i64 lo = (n - ((i64)kv + 2 * GW_THREADS) > 0) ? n - ((i64)kv + 2 * GW_THREADS) : 0;
         for (i64 r = lo + tid; r < n; r += GW_THREADS) RGW(r) = x[r];
         __syncthreads();
@@ -355,21 +356,21 @@ gbtrs_wide_kernel(i64 n, int kl, int ku, const double *__restrict__ ab, i64 ldab
 
 template <int KPL, int KPU>
 static int launch_wide(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
-                       double *dB, i64 ldb)
+                       double *dB, i64 ldb, int skip_u)
 {
     int ring = 4096;
     while (ring < kl + ku + 1 + 3 * GW_THREADS) ring <<= 1;
     const size_t smem = (size_t)ring * sizeof(double);
     BMB_CUDA(h, cudaFuncSetAttribute(gbtrs_wide_kernel<KPL, KPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gbtrs_wide_kernel<KPL, KPU><<<(unsigned)nrhs, GW_THREADS, smem, h->stream>>>(n, (int)kl, (int)ku, dAB, ldab, d_ipiv,
-                                                                                 dB, ldb, ring);
+                                                                                 dB, ldb, ring, skip_u);
     BMB_LAUNCH_CHECK(h);
     return 0;
 }
 
 template <int NR, int KPL, int SB>
 static int launch_n(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, const i64 *d_ipiv,
-                    double *dB, i64 ldb)
+                    double *dB, i64 ldb, int skip_u)
 {
     const i64 kv = kl + ku;
     int ring = 128;
@@ -384,7 +385,7 @@ static int launch_n(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const double
     const i64 tiles = cdiv64(nrhs, NR);
     const i64 blocks = cdiv64(tiles, GBTRS_WARPS);
     gbtrs_n_kernel<NR, KPL, SB><<<(unsigned)blocks, GBTRS_WARPS * 32, smem, h->stream>>>(n, (int)kl, (int)ku, nrhs, dAB,
-                                                                                        ldab, d_ipiv, dB, ldb, ring);
+                                                                                        ldab, d_ipiv, dB, ldb, ring, skip_u);
     BMB_LAUNCH_CHECK(h);
     return 0;
 }
@@ -438,14 +439,30 @@ extern "C" int bmb200_dgbtrs(bmb200_handle_t h, char trans, int64_t n, int64_t k
     const i64 need_u = cdiv64(imax64(0, kl + ku - 32), 64);
     if (need_u > need) need = need_u;
     if (need < 1) need = 1;
+    // Factors WITH interchanges beyond the register-window kernels.  Only the L sweep involves the pivots: the generic kernels
+    // below run it alone (skip_u) and the U sweep -- a plain upper-triangular band solve, DTBSV('U','N','N') -- goes through the
+    // cluster pipeline like an interchange-free solve (~69 instead of ~600-850 ns per column), bit-identical as before.
+    const i64 kvv = kl + ku;
+    const int split = (kl > 0 && n > 1 && !h->tune.gbtrs_nosplit) ? 1 : 0;
+    int rcl;
     // few right-hand sides per warp when there are few in total, so that more SMs take part
-    if (need <= 1) return (nrhs >= 1024) ? launch_n<4, 1, 8>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb)
-                                         : launch_n<1, 1, 8>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (need <= 2) return launch_n<2, 2, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (need <= 4) return launch_n<2, 4, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    if (need <= 1) rcl = (nrhs >= 1024) ? launch_n<4, 1, 8>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb, split)
+                                        : launch_n<1, 1, 8>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb, split);
+    else if (need <= 2) rcl = launch_n<2, 2, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb, split);
+    else if (need <= 4) rcl = launch_n<2, 4, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb, split);
     // wide bands with interchanges: one CTA per right-hand side
-    if (kl <= GW_THREADS && kl + ku <= 2 * GW_THREADS) return launch_wide<1, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
-    if (kl <= 2 * GW_THREADS && kl + ku <= 4 * GW_THREADS) return launch_wide<2, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb);
+    else if (kl <= GW_THREADS && kl + ku <= 2 * GW_THREADS) rcl = launch_wide<1, 2>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb, split);
+    else if (kl <= 2 * GW_THREADS && kl + ku <= 4 * GW_THREADS) rcl = launch_wide<2, 4>(h, n, kl, ku, nrhs, dAB, ldab, d_ipiv, dB, ldb, split);
+    else rcl = 1;
+    if (rcl == 0 && split) {
+        const int rcu = bmb_cluster_solve(h, 0, n, 0, kvv, nrhs, dAB, ldab, dB, ldb);  // U x = y
+        if (rcu == 1) {  // the pipeline does not take this shape: the U sweep of the generic kernels (kl = 0: their L sweep is empty)
+            if (need <= 4) return launch_n<2, 4, 2>(h, n, 0, kvv, nrhs, dAB, ldab, d_ipiv, dB, ldb, 0);
+            return launch_wide<2, 4>(h, n, 0, kvv, nrhs, dAB, ldab, d_ipiv, dB, ldb, 0);
+        }
+        return rcu;
+    }
+    if (rcl != 1) return rcl;
     snprintf(h->err, sizeof(h->err), "dgbtrs: band (%lld,%lld) wider than (2048, 4096-kl) is not supported", (long long)kl,
              (long long)ku);
     return BMB200_ERR_CUDA;
