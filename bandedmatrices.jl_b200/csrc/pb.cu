@@ -594,12 +594,25 @@ __global__ void pb_reverse_rows(i64 n, i64 nrhs, double *__restrict__ b, i64 ldb
 // Non-unit triangular band solve T x = b ('N') for narrow bands through the multi-RHS back substitution of bmb200_dgbtrs (kl = 0,
 // identity pivots): 'U' directly -- DGBTRS' U sweep IS dtbsv('U','N','N') -- and 'L' as the upper-triangular solve of the
 // reversed system (same operations in the same order per entry: bit-identical to dtbsv('L','N','N')).  Used by bmb200_dtbsv.
-int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, int tr, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
+__global__ void pb_unit_diag(i64 n, int k, double *__restrict__ m)  // 'U' storage, ld = k+1: the diagonal is band row k
+{
+    for (i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) m[k + j * (k + 1)] = 1.0;
+}
+__global__ void pb_copy_band(i64 n, int rows, const double *__restrict__ src, i64 lds, double *__restrict__ dst)
+{
+    const i64 total = n * rows;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 j = e / rows;
+        dst[e] = src[(e - j * rows) + j * lds];
+    }
+}
+
+int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, int tr, int unit, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
 {
     // op(T) upper: ('U','N') as stored; ('L','T') after a band transpose.  op(T) lower: reversed system -- ('L','N') from L,
     // ('U','T') from U^T (gather modes 1 / 0 of pb_reverse_factor).  The transposed forms run as column sweeps: equal to the
     // dot-product dtbsv('T') to rounding (1e-13), the 'N' forms bit for bit.
-    const bool direct = up && !tr;
+    const bool direct = up && !tr && !unit;  // a unit diagonal is made explicit in a copy (dividing by 1.0 is exact)
     const size_t fbytes = direct ? 0 : (size_t)n * (size_t)(k + 1) * sizeof(double), need = fbytes + (size_t)n * sizeof(i64);
     if (need > h->backup_bytes) {
         if (h->backup) { cudaStreamSynchronize(h->stream); cudaFree(h->backup); h->backup = nullptr; h->backup_bytes = 0; }
@@ -611,15 +624,24 @@ int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, int tr, i64 n, i64 k, i64 nrh
     pb_iota<<<(unsigned)imin64(cdiv64(n, 256), (i64)h->sm_count * 8), 256, 0, h->stream>>>(n, idp);
     BMB_LAUNCH_CHECK(h);
     if (direct) return bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, dA, lda, idp, dB, ldb);
-    if (!up && tr) {  // L^T: upper, in 'U' storage after the band transpose
-        const int rc = bmb200_dband_transpose(h, n, n, k, 0, dA, lda, M, k + 1);
-        return rc ? rc : bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, M, k + 1, idp, dB, ldb);
-    }
     const unsigned gb = (unsigned)imin64(cdiv64(n * (k + 1), 256), (i64)h->sm_count * 16);
+    const unsigned gd = (unsigned)imin64(cdiv64(n, 256), (i64)h->sm_count * 8);
+    if ((up != 0) != (tr != 0)) {  // op(T) is upper triangular: ('U','N') with a unit diagonal, or ('L','T') = L^T after the band transpose
+        if (up) {
+            pb_copy_band<<<gb, 256, 0, h->stream>>>(n, (int)k + 1, dA, lda, M);
+            BMB_LAUNCH_CHECK(h);
+        } else {
+            const int rc = bmb200_dband_transpose(h, n, n, k, 0, dA, lda, M, k + 1);
+            if (rc) return rc;
+        }
+        if (unit) { pb_unit_diag<<<gd, 256, 0, h->stream>>>(n, (int)k, M); BMB_LAUNCH_CHECK(h); }
+        return bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, M, k + 1, idp, dB, ldb);
+    }
     const unsigned gr = (unsigned)imin64(cdiv64(imax64(1, (n / 2) * nrhs), 256), (i64)h->sm_count * 16);
     pb_reverse_factor<<<gb, 256, 0, h->stream>>>(up ? 0 : 1, n, (int)k, dA, lda, M);
+    if (unit) pb_unit_diag<<<gd, 256, 0, h->stream>>>(n, (int)k, M);
     pb_reverse_rows<<<gr, 256, 0, h->stream>>>(n, nrhs, dB, ldb);
-    h->launches += 2;
+    h->launches += 2 + (unit ? 1 : 0);
     BMB_CUDA(h, cudaGetLastError());
     const int rc = bmb200_dgbtrs(h, 'N', n, 0, k, nrhs, M, k + 1, idp, dB, ldb);
     if (rc) return rc;
@@ -673,7 +695,7 @@ int bmb_gbtrs_t_fast(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doubl
     *u_done = *l_done = 0;
     if (n < 2) return 0;
     const i64 kv = kl + ku;
-    int rc = (kv <= 63) ? bmb_tri_solve_via_gbtrs(h, 1, 1, n, kv, nrhs, dAB, ldab, dB, ldb) : bmb_tri_solve_transposed_wide(h, 1, n, kv, nrhs, dAB, ldab, dB, ldb);
+    int rc = (kv <= 63) ? bmb_tri_solve_via_gbtrs(h, 1, 1, 0, n, kv, nrhs, dAB, ldab, dB, ldb) : bmb_tri_solve_transposed_wide(h, 1, n, kv, nrhs, dAB, ldab, dB, ldb);
     if (rc == 1) return 0;  // the cluster pipeline does not take this shape: everything is left to the caller
     if (rc) return rc;
     *u_done = 1;
@@ -865,8 +887,8 @@ extern "C" int bmb200_dpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
             if (rc == 0) rc = bmb_tri_solve_transposed_wide(h, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
         }
     } else {
-        rc = bmb_tri_solve_via_gbtrs(h, up, up ? 1 : 0, n, kd, nrhs, dAB, ldab, dB, ldb);
-        if (rc == 0) rc = bmb_tri_solve_via_gbtrs(h, up, up ? 0 : 1, n, kd, nrhs, dAB, ldab, dB, ldb);
+        rc = bmb_tri_solve_via_gbtrs(h, up, up ? 1 : 0, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
+        if (rc == 0) rc = bmb_tri_solve_via_gbtrs(h, up, up ? 0 : 1, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
         return rc;
     }
     if (rc == 1) {

@@ -9,7 +9,7 @@
 //     descending ('L') -- the per-row order of OpenBLAS' column sweep -- into a scratch vector, then copied back.
 #include "common.cuh"
 
-int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, int tr, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);  // pb.cu
+int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, int tr, int unit, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);  // pb.cu
 int bmb_tri_solve_transposed_wide(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);    // pb.cu
 int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
 
@@ -351,8 +351,8 @@ extern "C" int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag,
     if (!(trans == 'N' || trans == 'n')) {
         // non-unit transposed solves run as column sweeps on a transposed (wide) or reversed / transposed (narrow) copy of the
         // factor: the single-warp chain of dot products costs 250 ns (k = 4) to 2 us (k = 1024) per column
+        if (k <= 63 && n > 1) return bmb_tri_solve_via_gbtrs(h, up, 1, unit, n, k, 1, dA, lda, dx, n);
         if (!unit && n > 1) {
-            if (k <= 63) return bmb_tri_solve_via_gbtrs(h, up, 1, n, k, 1, dA, lda, dx, n);
             const int rc = bmb_tri_solve_transposed_wide(h, up, n, k, 1, dA, lda, dx, n);
             if (rc != 1) return rc;
         }
@@ -360,7 +360,7 @@ extern "C" int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag,
     }
     // narrow bands, non-unit diagonal: the multi-RHS back substitution of bmb200_dgbtrs (register-window kernels, ~45 ns per
     // column) instead of the cluster pipeline, which is built for wide bands (~250 ns per column at k = 4); pb.cu
-    if (!unit && k <= 63 && n > 1) return bmb_tri_solve_via_gbtrs(h, up, 0, n, k, 1, dA, lda, dx, n);
+    if (k <= 63 && n > 1) return bmb_tri_solve_via_gbtrs(h, up, 0, unit, n, k, 1, dA, lda, dx, n);
     // 'U': diagonal in row k of the band array, reach k above it (mode 0 with kl = 0 divides, mode 1 does not);
     // 'L': diagonal in row 0, reach k below it (mode 2 unit, mode 3 dividing)
     const int mode = up ? (unit ? 1 : 0) : (unit ? 2 : 3);
