@@ -653,7 +653,7 @@ int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, int tr, int unit, i64 n, i64 
 // The transposed non-unit solve for WIDE bands: the factor is transposed once on the device (one HBM pass into grow-only
 // workspace) and the sweep runs as a column sweep through the cluster pipeline (the chain of n dependent dot products of the
 // dtbsv('T') kernel costs ~2 us per column at k = 1024).  Returns 1 if the cluster pipeline does not take the shape.
-int bmb_tri_solve_transposed_wide(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
+int bmb_tri_solve_transposed_wide(bmb200_ctx *h, int up, int unit, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb)
 {
     const size_t need = (size_t)n * (size_t)(k + 1) * sizeof(double);
     if (need > h->backup_bytes) {
@@ -664,8 +664,8 @@ int bmb_tri_solve_transposed_wide(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs,
     double *tr = (double *)h->backup;
     const int rc = bmb200_dband_transpose(h, n, n, up ? 0 : k, up ? k : 0, dA, lda, tr, k + 1);
     if (rc) return rc;
-    // U^T = lower triangular ('L' storage, dividing: mode 3); L^T = upper triangular ('U' storage, dividing: mode 0)
-    return up ? bmb_cluster_solve(h, 3, n, k, 0, nrhs, tr, k + 1, dB, ldb) : bmb_cluster_solve(h, 0, n, 0, k, nrhs, tr, k + 1, dB, ldb);
+    // U^T = lower triangular ('L' storage: mode 3 dividing, 2 unit); L^T = upper triangular ('U' storage: mode 0 dividing, 1 unit)
+    return up ? bmb_cluster_solve(h, unit ? 2 : 3, n, k, 0, nrhs, tr, k + 1, dB, ldb) : bmb_cluster_solve(h, unit ? 1 : 0, n, 0, k, nrhs, tr, k + 1, dB, ldb);
 }
 
 // ---- ldiv!(transpose(F), B) (src/banded/linalg.jl:41-47 -> dgbtrs_('T')): U^T y = b, then L^T x = y with the interchanges undone.
@@ -695,7 +695,7 @@ int bmb_gbtrs_t_fast(bmb200_ctx *h, i64 n, i64 kl, i64 ku, i64 nrhs, const doubl
     *u_done = *l_done = 0;
     if (n < 2) return 0;
     const i64 kv = kl + ku;
-    int rc = (kv <= 63) ? bmb_tri_solve_via_gbtrs(h, 1, 1, 0, n, kv, nrhs, dAB, ldab, dB, ldb) : bmb_tri_solve_transposed_wide(h, 1, n, kv, nrhs, dAB, ldab, dB, ldb);
+    int rc = (kv <= 63) ? bmb_tri_solve_via_gbtrs(h, 1, 1, 0, n, kv, nrhs, dAB, ldab, dB, ldb) : bmb_tri_solve_transposed_wide(h, 1, 0, n, kv, nrhs, dAB, ldab, dB, ldb);
     if (rc == 1) return 0;  // the cluster pipeline does not take this shape: everything is left to the caller
     if (rc) return rc;
     *u_done = 1;
@@ -880,11 +880,11 @@ extern "C" int bmb200_dpbtrs(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
     int rc;
     if (kd >= PB_TRANSPOSE_KD) {
         if (up) {
-            rc = bmb_tri_solve_transposed_wide(h, 1, n, kd, nrhs, dAB, ldab, dB, ldb);
+            rc = bmb_tri_solve_transposed_wide(h, 1, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
             if (rc == 0) rc = bmb_cluster_solve(h, 0, n, 0, kd, nrhs, dAB, ldab, dB, ldb);
         } else {
             rc = bmb_cluster_solve(h, 3, n, kd, 0, nrhs, dAB, ldab, dB, ldb);
-            if (rc == 0) rc = bmb_tri_solve_transposed_wide(h, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
+            if (rc == 0) rc = bmb_tri_solve_transposed_wide(h, 0, 0, n, kd, nrhs, dAB, ldab, dB, ldb);
         }
     } else {
         rc = bmb_tri_solve_via_gbtrs(h, up, up ? 1 : 0, 0, n, kd, nrhs, dAB, ldab, dB, ldb);

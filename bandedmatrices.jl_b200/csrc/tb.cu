@@ -10,7 +10,7 @@
 #include "common.cuh"
 
 int bmb_tri_solve_via_gbtrs(bmb200_ctx *h, int up, int tr, int unit, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);  // pb.cu
-int bmb_tri_solve_transposed_wide(bmb200_ctx *h, int up, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);    // pb.cu
+int bmb_tri_solve_transposed_wide(bmb200_ctx *h, int up, int unit, i64 n, i64 k, i64 nrhs, const double *dA, i64 lda, double *dB, i64 ldb);  // pb.cu
 int bmb_cluster_solve(bmb200_ctx *h, int mode, i64 n, i64 kl, i64 ku, i64 nrhs, const double *dAB, i64 ldab, double *dB, i64 ldb);  // gbtrs_cluster.cu
 
 __global__ void __launch_bounds__(256)
@@ -352,8 +352,8 @@ extern "C" int bmb200_dtbsv(bmb200_handle_t h, char uplo, char trans, char diag,
         // non-unit transposed solves run as column sweeps on a transposed (wide) or reversed / transposed (narrow) copy of the
         // factor: the single-warp chain of dot products costs 250 ns (k = 4) to 2 us (k = 1024) per column
         if (k <= 63 && n > 1) return bmb_tri_solve_via_gbtrs(h, up, 1, unit, n, k, 1, dA, lda, dx, n);
-        if (!unit && n > 1) {
-            const int rc = bmb_tri_solve_transposed_wide(h, up, n, k, 1, dA, lda, dx, n);
+        if (n > 1) {
+            const int rc = bmb_tri_solve_transposed_wide(h, up, unit, n, k, 1, dA, lda, dx, n);
             if (rc != 1) return rc;
         }
         return bmb_tbsv_t_multi(h, up, unit, n, k, 1, dA, lda, dx, n > 1 ? n : 1);

@@ -76,7 +76,7 @@ def _narrow_case(bm, oracle_c, rng, n, kd):
         assert np.array_equal(x.cpu().numpy(), gotb[:, 0])
 
 
-@pytest.mark.parametrize("shape", [(300, 65), (1000, 100), (700, 128), (2000, 300), (3000, 1024), (500, 499), (130, 129), (4096, 64 * 3)])
+@pytest.mark.parametrize("shape", [(300, 65), (66, 65), (1000, 100), (700, 128), (2000, 300), (3000, 1024), (500, 499), (130, 129), (4096, 64 * 3)])
 def test_pbtrf_wide_blocked(bm, oracle_ob, rng, shape):
     n, kd = shape
     for uplo, extra in itertools.product("UL", (0, 1)):

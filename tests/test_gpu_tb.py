@@ -22,7 +22,7 @@ def _dev(a):
 
 
 @pytest.mark.parametrize("shape", [(1, 0), (5, 2), (40, 3), (1000, 16), (4097, 40), (30000, 7), (6000, 300), (50, 80),
-                                   (20011, 1024), (3000, 1500)])
+                                   (20011, 1024), (3000, 1500), (2, 1), (700, 63), (700, 64), (129, 127)])
 def test_tbsv_tbmv_bit_identical(bm, oracle_c, rng, shape):
     n, k = shape
     for uplo, diag, extra in itertools.product("UL", "NU", (0, 3)):
@@ -38,7 +38,8 @@ def test_tbsv_tbmv_bit_identical(bm, oracle_c, rng, shape):
             assert np.array_equal(x.cpu().numpy(), ref), (name, uplo, diag, n, k, extra)
 
 
-@pytest.mark.parametrize("shape", [(1, 0), (5, 2), (40, 3), (1000, 16), (4097, 40), (30000, 7), (3000, 300), (50, 80), (2500, 1024)])
+@pytest.mark.parametrize("shape", [(1, 0), (5, 2), (40, 3), (1000, 16), (4097, 40), (30000, 7), (3000, 300), (50, 80), (2500, 1024),
+                                   (2, 1), (700, 63), (700, 64), (3000, 1500)])
 def test_tbsv_tbmv_transposed(bm, oracle_c, rng, shape):
     """trans = 'T' (row-major layouts, src/tribanded.jl:86-96): dot-product forms; OpenBLAS' own summation order is
     unspecified there, so the comparison with the oracle is to 1e-13 (relative to max|x|), like the other 'T' paths."""
