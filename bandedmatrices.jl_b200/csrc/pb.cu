@@ -232,25 +232,85 @@ pbtf2_diag(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restri
 __device__ __forceinline__ void pb_lds2(unsigned addr, double &x, double &y) { asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr)); }
 __device__ __forceinline__ void pb_sts2(unsigned addr, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(x), "d"(y) : "memory"); }
 
+#ifdef PB_DEBUG_TIMING
+__device__ long long pb_stamps[4][8][2];
+__device__ unsigned long long pb_lastend[4][2];  // latest end over ALL CTAs of the panel kernel / the update kernel
+#define PB_STAMP_END(which, panel)                                                                  \
+    do {                                                                                            \
+        if (threadIdx.x == 0 && (panel) >= 10 && (panel) <= 13) {                                   \
+            unsigned long long t_;                                                                  \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                  \
+            atomicMax(&pb_lastend[(panel) - 10][which], t_);                                        \
+        }                                                                                           \
+    } while (0)
+#define PB_STAMP(ev, panel)                                                                         \
+    do {                                                                                            \
+        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (panel) >= 10 && (panel) <= 13) {  \
+            long long t_;                                                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                  \
+            pb_stamps[(panel) - 10][ev][blockIdx.x == 0 ? 0 : 1] = t_;                              \
+            if ((panel) == 13 && ev == 6 && blockIdx.x == 0)                                        \
+                for (int p_ = 0; p_ < 4; ++p_)                                                      \
+                    for (int e_ = 0; e_ < 7; ++e_)                                                  \
+                        printf("STAMP %d %d %lld %lld  last k1 %lld k3 %lld\n", p_ + 10, e_, pb_stamps[p_][e_][0] - pb_stamps[0][0][0], pb_stamps[p_][e_][1] - pb_stamps[0][0][0], (long long)pb_lastend[p_][0] - pb_stamps[0][0][0], (long long)pb_lastend[p_][1] - pb_stamps[0][0][0]); \
+        }                                                                                           \
+    } while (0)
+#else
+#define PB_STAMP(what, panel) do { } while (0)
+#define PB_STAMP_END(which, panel) do { } while (0)
+#endif
+#define PB_TPC 16  // lanes per column of A12 in the substitution
+// Since the fusion of K1 and K2 this kernel is launched with one CTA per 16 columns of A12: EVERY CTA factors the diagonal block
+// (redundantly -- the chain is the critical path anyway and the SMs are otherwise idle), keeps U11 in its shared memory and goes
+// straight on to the substitution for its own columns: one launch, one dependent global round trip and the staging of U11 less per
+// panel.  CTA 0 only factors and publishes: the factored block goes back into the matrix once every CTA of the grid has the
+// unfactored block in its registers (arrival counter d_state[3]; only CTA 0 ever waits, so CTAs of a grid larger than one wave
+// still get their turn), while the other CTAs are already substituting.
 __global__ void __launch_bounds__(PB_K1T)
-pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, double *__restrict__ d_rdiag)
+pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, int q)
 {
+    __shared__ __align__(16) double u11[PB_NB * PB_NB];  // U11(i,t) at [i*NB + t] for t > i, else 0 (trsm phase)
     __shared__ __align__(16) double xs[2][4][PB_NB];  // the four scaled rows of a row group, [row group parity][row][column]
     __shared__ double rd[PB_NB + 1];
     __shared__ __align__(16) double dpatch[16];        // the diagonal 4 x 4 patch of the current row group
-    __shared__ int s_panel, s_fail;
+    __shared__ int s_fail;
     // programmatic dependent launch (the three kernels of a panel are captured with it): this grid was launched while its
     // predecessor was still running; nothing is read before the predecessor has completed and flushed, and the successor may
     // be launched right away so that its launch latency hides behind this grid
+    // The panel is d_state[1] + q: q is this launch's place in the captured graph, d_state[1] the first panel of the replay --
+    // written only by the LAST pb_syrk of the previous replay, so it may be read before the wait.  The info word is loaded
+    // after the wait together with the block; the exit on it comes once those loads are in flight.
+    int base;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(base) : "l"(d_state + 1));
+    const int s_panel = base + q;
+    const i64 j0 = (i64)s_panel * PB_NB;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (d_state[0] != 0) return;
-    if (threadIdx.x == 0) { s_panel = d_state[1] + 1; d_state[1] = s_panel; s_fail = 0; }
-    __syncthreads();
-    const i64 j0 = (i64)s_panel * PB_NB;
     if (j0 >= n_total) return;
+    int info0;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(info0) : "l"(d_state) : "memory");
+    if (threadIdx.x == 0) s_fail = 0;
+    PB_STAMP(0, s_panel);
     const int nbl = (int)imin64_d(PB_NB, n_total - j0);
+    if (nbl < PB_NB)  // a partial last panel: the substitution reads columns the factorisation never writes
+        for (int e = threadIdx.x; e < PB_NB * PB_NB; e += PB_K1T) u11[e] = 0.0;
+    __syncthreads();
     double *p = p0 + j0 * (si + sk);  // U(j0, j0)
+    // substitution phase, prepared now: CTA 0 only factors and publishes, CTA c >= 1 takes 16 columns of A12, 16 lanes per column,
+    // lane tq holding the panel rows 4tq .. 4tq+3 of its column (they do not depend on the factorisation)
+    const i64 c1 = j0 + nbl;                            // first column right of the panel
+    const i64 ncols12 = imin64_d(kd, n_total - c1);     // columns of A12 (row j0+nbl-1 reaches c1-1+kd)
+    const int tq = threadIdx.x % PB_TPC;
+    const i64 tcol = ((i64)blockIdx.x - 1) * (PB_K1T / PB_TPC) + threadIdx.x / PB_TPC;
+    const bool tlive = blockIdx.x > 0 && tcol < ncols12;
+    const i64 tk = c1 + (tlive ? tcol : 0);
+    const int ti0 = (int)imax64_d(0, tk - kd - j0);     // first stored panel row of column tk
+    double ta[4];
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) {
+        const int i = 4 * tq + s2;
+        ta[s2] = (tlive && i >= ti0 && i < nbl) ? p0[(j0 + i) * si + tk * sk] : 0.0;
+    }
     // the compiler otherwise re-reads %tid and rebuilds the shared-window base (S2R / S2UR, tens of cycles each) inside every
     // step, right on the dependency chain: read them once through volatile asm so that they have to stay in registers
     int tid;
@@ -277,10 +337,7 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
     asm volatile("mov.u32 %0, %0;" : "+r"(xr_a));
     asm volatile("mov.u32 %0, %0;" : "+r"(xc_a));
     int failed = 0;
-#ifdef PB_DEBUG_TIMING
-    long long dbg_c0 = clock64(), dbg_t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
-#endif
+    if (info0 != 0) return;  // an earlier panel was not positive definite
 #pragma unroll 1
     for (int jb = 0; jb < PB_NB / 4 && 4 * jb < nbl; ++jb) {
         const bool inwarp = warp == ((jb * PB_LG) >> 5);  // this warp holds rows 4jb..4jb+3
@@ -385,91 +442,92 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
         if (nextwarp) asm volatile("bar.arrive 1, %0;" ::"n"(PB_K1T) : "memory");
     }
     __syncthreads();
+    PB_STAMP(1, s_panel);
+    if (tid == 0) atomicAdd(&d_state[3], 1);  // every value loaded from the block has been consumed: CTA 0 may overwrite it
     if (!failed) {
         int f;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(fl0));
         failed = f;
     }
-#ifdef PB_DEBUG_TIMING
-    if (tid == 0 && s_panel == 10) {
-        long long dbg_t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
-        printf("pb_potf2_reg panel 10: step loop %lld cycles, %lld ns\n", clock64() - dbg_c0, dbg_t1 - dbg_t0);
+    auto publish = [&]() {  // CTA 0: the block as it stands in the registers goes back into the matrix
+        if (tid == 0) {
+            const volatile int *cnt = d_state + 3;
+            while (*cnt < (int)gridDim.x) { }
+            __threadfence();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int r = 4 * a + u, c = 4 * b + w;
+                if (upper && r <= c && c < nbl && c - r <= kd) p[(i64)r * si + (i64)c * sk] = v[u][w];
+            }
+    };
+    if (failed) {  // not positive definite: the block as updated so far goes back (CTA 0), the panel counter stops
+        if (blockIdx.x == 0) {
+            if (tid == 0) d_state[0] = (int)(j0 + failed);
+            publish();
+        }
+        return;
     }
-#endif
-    if (failed && tid == 0) d_state[0] = (int)(j0 + failed);
-    if (tid < nbl) d_rdiag[tid] = rd[tid];
-    // the factor (also the partially updated block after a failure, as DPBTF2 leaves it)
+    if (blockIdx.x == 0) {  // the publisher: its write-back overlaps the other CTAs' substitution
+        publish();
+        PB_STAMP(3, s_panel);
+        return;
+    }
+    if (ncols12 <= 0) return;
+    // the factor above the diagonal: into this CTA's shared memory for the substitution
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const int r = 4 * a + u, c = 4 * b + w;
-            if (upper && r <= c && c < nbl && c - r <= kd) p[(i64)r * si + (i64)c * sk] = v[u][w];
+            if (upper && r < c && c < nbl) u11[r * PB_NB + c] = v[u][w];
         }
-}
-
-// K2: U12 = U11^{-T} A12.  Rows = the panel's NB rows j0..j0+nbl-1, columns = the kd columns right of the panel.  PB_TPC
-// lanes per column (lane q holds rows q, q+TPC, ...: NB/TPC registers; many threads with few FMAs each, because a warp issues
-// FP64 FMAs slowly and the work is only a few MFLOP), right-looking substitution: u_i = a_i / U11(i,i) is
-// broadcast by a shuffle, every lane updates its rows t > i.  U11 sits in shared memory with its diagonal moved to a
-// reciprocal array and zeros on and below the diagonal, so the update needs no predicate.  A column's entries above the band
-// (row i reaches column i+kd only) are not stored and count as zero.
-#define PB_TPC 16
-__global__ void __launch_bounds__(256)
-pb_trsm(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__restrict__ d_state, const double *__restrict__ d_rdiag)
-{
-    extern __shared__ double pb_sm2[];
-    double *u11 = pb_sm2;                       // U11(i,t) at [i*NB + t] for t > i, else 0
-    double *rdiag = pb_sm2 + PB_NB * PB_NB;
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (d_state[0] != 0) return;
-    const i64 j0 = (i64)d_state[1] * PB_NB;
-    if (j0 >= n) return;
-    const int nbl = (int)imin64_d(PB_NB, n - j0);
-    const i64 c1 = j0 + nbl;                       // first column right of the panel
-    const i64 ncols = imin64_d(kd, n - c1);        // columns of A12 (row j0+nbl-1 reaches c1-1+kd)
-    if (ncols <= 0) return;
-    double *p = p0;
-    for (int e = threadIdx.x; e < PB_NB * PB_NB; e += blockDim.x) {  // all copies in flight at once
-        int i, t;
-        if (si == 1) { i = e % PB_NB; t = e / PB_NB; } else { t = e % PB_NB; i = e / PB_NB; }
-        const bool ok = i < nbl && t < nbl && i < t;
-        cp_async8_zfill(u11 + i * PB_NB + t, p + (j0 + (ok ? i : 0)) * si + (j0 + (ok ? t : 0)) * sk, ok);
-    }
-    if (threadIdx.x < PB_NB) cp_async8_zfill(rdiag + threadIdx.x, d_rdiag + threadIdx.x, (int)threadIdx.x < nbl);
-    cp_async_commit();
-    // this thread's part of its column of A12 does not depend on the staged block: the loads overlap the copies
-    const int q = threadIdx.x % PB_TPC;
-    const i64 c = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / PB_TPC;
-    const bool live = c < ncols;  // dead lanes keep shuffling
-    const i64 k = c1 + (live ? c : 0);
-    // first stored panel row of column k: k <= (j0+i) + kd  =>  i >= k - kd - j0
-    const int i0 = (int)imax64_d(0, k - kd - j0);
-    double a[PB_NB / PB_TPC];
-#pragma unroll
-    for (int s = 0; s < PB_NB / PB_TPC; ++s) {
-        const int i = s * PB_TPC + q;
-        a[s] = (live && i >= i0 && i < nbl) ? p[(j0 + i) * si + k * sk] : 0.0;
-    }
-    cp_async_wait<0>();
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31u, base = lane & ~(unsigned)(PB_TPC - 1);
+    // ---- substitution U12 = U11^{-T} A12 for this CTA's columns, four rows (one row group g) per step: every lane runs the
+    // 4 x 4 forward substitution of the group on its own registers (only the owner's, lane g, is meaningful), the owner's four
+    // results are broadcast by shuffles, and the lanes below apply them to their four rows.  Per entry the subtractions come in
+    // ascending row order, each one FMA -- the order of the column-at-a-time substitution.
+    {
+        const unsigned tbase = (unsigned)lane & ~(unsigned)(PB_TPC - 1);
 #pragma unroll
-    for (int i = 0; i < PB_NB; ++i) {
-        const double mine = __dmul_rn(a[i / PB_TPC], rdiag[i]);
-        const double ui = __shfl_sync(0xffffffffu, mine, base + (i % PB_TPC));
-        if (q == i % PB_TPC) a[i / PB_TPC] = ui;
-        const double *urow = u11 + i * PB_NB + q;
+        for (int g = 0; g < PB_NB / 4; ++g) {
+            const double *ug = u11 + (4 * g) * PB_NB;
+            const double d01 = ug[4 * g + 1], d02 = ug[4 * g + 2], d03 = ug[4 * g + 3];
+            const double d12 = ug[PB_NB + 4 * g + 2], d13 = ug[PB_NB + 4 * g + 3], d23 = ug[2 * PB_NB + 4 * g + 3];
+            const double r0 = (4 * g + 0 < nbl) ? rd[4 * g + 0] : 0.0, r1 = (4 * g + 1 < nbl) ? rd[4 * g + 1] : 0.0;
+            const double r2 = (4 * g + 2 < nbl) ? rd[4 * g + 2] : 0.0, r3 = (4 * g + 3 < nbl) ? rd[4 * g + 3] : 0.0;
+            const double x0 = __dmul_rn(ta[0], r0);
+            const double x1 = __dmul_rn(fma(-d01, x0, ta[1]), r1);
+            const double x2 = __dmul_rn(fma(-d12, x1, fma(-d02, x0, ta[2])), r2);
+            const double x3 = __dmul_rn(fma(-d23, x2, fma(-d13, x1, fma(-d03, x0, ta[3]))), r3);
+            const unsigned src = tbase + g;
+            const double b0 = __shfl_sync(0xffffffffu, x0, src), b1 = __shfl_sync(0xffffffffu, x1, src);
+            const double b2 = __shfl_sync(0xffffffffu, x2, src), b3 = __shfl_sync(0xffffffffu, x3, src);
+            if (tq == g) { ta[0] = x0; ta[1] = x1; ta[2] = x2; ta[3] = x3; }
+            if (tq > g) {
 #pragma unroll
-        for (int s = i / PB_TPC; s < PB_NB / PB_TPC; ++s) a[s] = fma(-urow[s * PB_TPC], ui, a[s]);
+                for (int r = 0; r < 4; ++r) {
+                    const double2 ulo = *reinterpret_cast<const double2 *>(ug + r * PB_NB + 4 * tq);
+                    const double2 uhi = *reinterpret_cast<const double2 *>(ug + r * PB_NB + 4 * tq + 2);
+                    const double br = (r == 0) ? b0 : (r == 1) ? b1 : (r == 2) ? b2 : b3;
+                    ta[0] = fma(-ulo.x, br, ta[0]);
+                    ta[1] = fma(-ulo.y, br, ta[1]);
+                    ta[2] = fma(-uhi.x, br, ta[2]);
+                    ta[3] = fma(-uhi.y, br, ta[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+            const int i = 4 * tq + s2;
+            if (tlive && i >= ti0 && i < nbl) p0[(j0 + i) * si + tk * sk] = ta[s2];
+        }
     }
-#pragma unroll
-    for (int s = 0; s < PB_NB / PB_TPC; ++s) {
-        const int i = s * PB_TPC + q;
-        if (live && i >= i0 && i < nbl) p[(j0 + i) * si + k * sk] = a[s];
-    }
+    PB_STAMP(2, s_panel);
+    PB_STAMP_END(0, s_panel);
 }
 
 // K3: A22(r,c) -= sum_i U12(i,r) U12(i,c) for r <= c inside the window of kd columns right of the panel.  One CTA per 64 x 64
@@ -486,16 +544,25 @@ __device__ __forceinline__ void pb_dmma884(double &d0, double &d1, double a, dou
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __global__ void __launch_bounds__(256)
-pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__restrict__ d_state, int ntile1d)
+pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, int ntile1d, int q, int bump)
 {
     extern __shared__ __align__(16) double pb_sm[];
     double *sr = pb_sm, *sc = pb_sm + PB_SLAB;
+    int base;  // see pb_potf2_reg
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(base) : "l"(d_state + 1));
+    const int panel = base + q;
+    const i64 j0 = (i64)panel * PB_NB;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (d_state[0] != 0) return;
-    const i64 j0 = (i64)d_state[1] * PB_NB;
     if (j0 >= n) return;
+    int info0;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(info0) : "l"(d_state) : "memory");
     const int nbl = (int)imin64_d(PB_NB, n - j0);
+    PB_STAMP(4, panel);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the arrival counter of the panel kernel back to zero; the last panel of a replay
+        d_state[3] = 0;                         // moves the base on for the next one
+        if (bump) d_state[1] = base + bump;
+    }
     const i64 c1 = j0 + nbl;
     const i64 ncols = imin64_d(kd, n - c1);
     if (ncols <= 0) return;
@@ -536,6 +603,8 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
         }
     cp_async_wait<0>();
     __syncthreads();
+    if (info0 != 0) return;  // the panel was not positive definite: nothing is written
+    PB_STAMP(5, panel);
     const double *scc = (tc != tr) ? sc : sr;
     const double *ap = sr + lc * SI + (warp * 8 + lr) * SX;  // A fragment: A[row = lane/4][k = lane%4] = U12(k0 + k, row)
     const double *bp = scc + lc * SI + lr * SX;              // B fragment: B[k = lane%4][col = lane/4] = U12(k0 + k, col)
@@ -555,6 +624,8 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, const int *__res
             const i64 cc = (i64)tc * 64 + t * 8 + 2 * lc + q;
             if (rr <= cc && cc < ncols) p[(c1 + rr) * si + (c1 + cc) * sk] = cv[t][q] - acc[t][q];
         }
+    PB_STAMP_END(1, panel);
+    PB_STAMP(6, panel);
 }
 
 // ---- helpers of the narrow-band dpbtrs: both sweeps run through the tuned multi-RHS back substitution of bmb200_dgbtrs ----
@@ -753,7 +824,7 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
     double *p0 = dAB + (up ? kd : 0);        // 'U': the diagonal lives in band row kd
     if (kd > n - 1) kd = n > 1 ? n - 1 : 0;  // bands beyond the matrix are never referenced (LAPACK: kn = min(kd, n-j))
     int *d_state = h->d_info + 24;
-    const int init[2] = {0, -1};
+    const int init[4] = {0, 0, 0, 0};  // info, first panel of the graph replay, -, arrival counter of the panel kernel
     BMB_CUDA(h, cudaMemcpyAsync(d_state, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     const bool blocked = kd > 64;
     long long *dstats = nullptr;  // (the cycle breakdown that guided the window kernel was removed with its clock reads)
@@ -790,13 +861,10 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
         BMB_LAUNCH_CHECK(h);
     } else {
         const i64 npanels = cdiv64(n, PB_NB);
-        if (bmb_ensure_scratch(h, 4096) != 0) return BMB200_ERR_CUDA;
-        double *d_rdiag = (double *)h->scratch;  // reciprocals of the panel's diagonal, K1 -> K2
         const int ntile1d = (int)cdiv64(imin64(kd, n), 64);
         const unsigned ntiles = (unsigned)(ntile1d * (ntile1d + 1) / 2);
         const unsigned trsm_blocks = (unsigned)cdiv64(imin64(kd, n) * PB_TPC, 256);
-        const size_t smem3 = (size_t)2 * PB_SLAB * sizeof(double), smem2 = (size_t)(PB_NB * PB_NB + PB_NB) * sizeof(double);
-        BMB_CUDA(h, cudaFuncSetAttribute(pb_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        const size_t smem3 = (size_t)2 * PB_SLAB * sizeof(double);
         BMB_CUDA(h, cudaFuncSetAttribute(pb_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         // one graph of PB_GRAPH_PANELS panels (K1, K2, K3 each), replayed; the kernels take the panel from d_state[1]
         cudaGraph_t graph = nullptr;
@@ -825,10 +893,9 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
             BMB_CUDA(h, cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
             ce = cudaSuccess;
             for (i64 q = 0; q < chunk && ce == cudaSuccess; ++q) {
-                cudaLaunchConfig_t c1c = cfg(1, PB_K1T, 0), c2c = cfg(trsm_blocks, 256, smem2), c3c = cfg(ntiles, 256, smem3);
-                ce = cudaLaunchKernelEx(&c1c, pb_potf2_reg, (i64)n, (int)kd, si, sk, p0, d_state, d_rdiag);
-                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c2c, pb_trsm, (i64)n, (int)kd, si, sk, p0, (const int *)d_state, (const double *)d_rdiag);
-                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c3c, pb_syrk, (i64)n, (int)kd, si, sk, p0, (const int *)d_state, ntile1d);
+                cudaLaunchConfig_t c1c = cfg(trsm_blocks + 1, PB_K1T, 0), c3c = cfg(ntiles, 256, smem3);
+                ce = cudaLaunchKernelEx(&c1c, pb_potf2_reg, (i64)n, (int)kd, si, sk, p0, d_state, (int)q);
+                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c3c, pb_syrk, (i64)n, (int)kd, si, sk, p0, d_state, ntile1d, (int)q, (int)(q == chunk - 1 ? chunk : 0));
             }
             const cudaError_t ee = cudaStreamEndCapture(gs, &graph);
             if (ce == cudaSuccess) ce = ee;
@@ -843,7 +910,7 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
             ce = cudaGraphLaunch(exec, gs);
             if (ce != cudaSuccess) break;
         }
-        h->launches += 3 * cdiv64(npanels, chunk) * chunk;
+        h->launches += 2 * cdiv64(npanels, chunk) * chunk;
         const cudaError_t se = cudaStreamSynchronize(gs);
         cudaGraphExecDestroy(exec);
         cudaGraphDestroy(graph);
