@@ -13,11 +13,10 @@
 //     cp.async, every thread recomputes the reciprocal itself (no broadcast step), one barrier per column.  Each entry receives
 //     its updates in ascending j exactly as the CPU does: factors are BIT-IDENTICAL to OpenBLAS dpbtrf_.
 // kd > 64 -- blocked right-looking (the structure of DPBTRF, NB = 64 here): per panel of NB columns
-//     K1 `pbtf2_window` on the NB x NB diagonal block, K2 `pb_trsm` U12 = U11^{-T} A12 (one thread per column of A12, the
-//     substitution kept in registers), K3 `pb_syrk` A22 -= U12^T U12 on the kd x kd window (64 x 64 tiles, 4 x 4 register tiles
-//     of FP64 FMAs -- on B200 the FP64 FMA pipe and DMMA have the same peak, profiles/fp64_peaks_r1.json).  The three kernels
-//     of a panel read the panel index from a device counter, so a CUDA graph of PB_GRAPH_PANELS panels is captured once per
-//     handle and replayed; panels past the end are no-ops.  DPBTRF's DGEMM/DSYRK order is unspecified: compared to
+//     `pb_potf2_reg`: the NB x NB diagonal block factored in registers by EVERY CTA of the grid, each of which then substitutes
+//     U12 = U11^{-T} A12 for its 16 columns of A12 (CTA 0 instead writes the factored block back); `pb_syrk`: A22 -= U12^T U12
+//     on the kd x kd window (64 x 64 tiles on DMMA.8x8x4).  The panel is (a device base counter) + (the launch's place in the
+//     graph), so a CUDA graph of PB_GRAPH_PANELS panels is captured once per call and replayed; panels past the end are no-ops.  DPBTRF's DGEMM/DSYRK order is unspecified: compared to
 //     OpenBLAS at 1e-13 * cond-ish tolerances and through ||U^T U - A||.
 // pbtrs -- DPBTRS = two DTBSV sweeps per right-hand side ('U': U^T then U; 'L': L then L^T), run for ALL right-hand sides at
 //     once (cluster pipeline of gbtrs_cluster.cu for the 'N' sweep, one chain block per right-hand side for the 'T' sweep).
@@ -228,7 +227,6 @@ pbtf2_diag(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restri
 // posts it in shared memory; one barrier; every patch right/below subtracts x_r x_c.  Per step the dependency chain is
 // shuffle + rsqrt + multiply + one shared-memory round trip + FMA (tools/fp64_issue.cu: ~30 + 72 + 10 + ~210 cycles); shared
 // memory is addressed through precomputed 32-bit addresses and nothing inside the step touches global or constant memory.
-// The reciprocal diagonal goes to d_rdiag for K2.
 __device__ __forceinline__ void pb_lds2(unsigned addr, double &x, double &y) { asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr)); }
 __device__ __forceinline__ void pb_sts2(unsigned addr, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(x), "d"(y) : "memory"); }
 
@@ -260,7 +258,7 @@ __device__ unsigned long long pb_lastend[4][2];  // latest end over ALL CTAs of 
 #define PB_STAMP_END(which, panel) do { } while (0)
 #endif
 #define PB_TPC 16  // lanes per column of A12 in the substitution
-// Since the fusion of K1 and K2 this kernel is launched with one CTA per 16 columns of A12: EVERY CTA factors the diagonal block
+// Since the fusion with the former substitution kernel this kernel is launched with one CTA per 16 columns of A12: EVERY CTA factors the diagonal block
 // (redundantly -- the chain is the critical path anyway and the SMs are otherwise idle), keeps U11 in its shared memory and goes
 // straight on to the substitution for its own columns: one launch, one dependent global round trip and the staging of U11 less per
 // panel.  CTA 0 only factors and publishes: the factored block goes back into the matrix once every CTA of the grid has the
@@ -866,7 +864,7 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
         const unsigned trsm_blocks = (unsigned)cdiv64(imin64(kd, n) * PB_TPC, 256);
         const size_t smem3 = (size_t)2 * PB_SLAB * sizeof(double);
         BMB_CUDA(h, cudaFuncSetAttribute(pb_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        // one graph of PB_GRAPH_PANELS panels (K1, K2, K3 each), replayed; the kernels take the panel from d_state[1]
+        // one graph of PB_GRAPH_PANELS panels (panel kernel + update kernel each), replayed; panel = d_state[1] + place in the graph
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         const i64 chunk = imin64(npanels, PB_GRAPH_PANELS);

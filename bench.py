@@ -41,15 +41,44 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: an in-process NVML poller (5 ms period; the timed region of
+    the default run is ~35 ms, too short for an `nvidia-smi -lms` child to get a sample in), nvidia-smi as the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.h = index, [], None, None, None
+        self.sm, self.reason_bits, self.mx, self.run = [], 0, None, False
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                pr = torch.cuda.get_device_properties(index)
+                self.h = nv.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nv is not None:
+            self.run = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -64,6 +93,15 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.run = False
+            self.t.join(timeout=1.0)
+            nv, bits = self.nv, self.reason_bits
+            table = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4)]
+            reasons = sorted(name for name, attr, dflt in table if bits & int(getattr(nv, attr, dflt)))
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(self.sm), "source": "nvml, 5 ms period, inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -73,7 +111,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -187,10 +225,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = hd.launches

@@ -472,7 +472,7 @@ def _c5_cholesky(bm, L, A, rhs, N, tpeak, tsrc):
     res.update({"info": int(info), "pbtrf_ms": round(t_f, 1), "pbtrf_TFLOPs": round(flops / t_f / 1e9, 3), "pbtrs_ms": round(t_s, 1), "flops": flops,
                 "roofline": {"bound": "tensor", "achieved": round(flops / t_f / 1e9, 3), "peak": tpeak, "unit": "TFLOP/s (FP64)",
                              "frac": round(flops / t_f / 1e9 / tpeak, 4), "traffic": None, "peak_source": tsrc,
-                             "kernel": "pb_potf2_reg + pb_trsm + pb_syrk (DMMA) per 64-column panel, CUDA graph"},
+                             "kernel": "pb_potf2_reg (factorisation + substitution) + pb_syrk (DMMA) per 64-column panel, CUDA graph"},
                 "parity": {"max_residual_over_max_x_full": float(r.abs().max() / x.abs().max())}})
     if L is not None:
         import oracle
