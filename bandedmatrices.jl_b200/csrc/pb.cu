@@ -542,35 +542,49 @@ __device__ __forceinline__ void pb_dmma884(double &d0, double &d1, double a, dou
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __global__ void __launch_bounds__(256)
-pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, int ntile1d, int q, int bump)
+pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, int ntile1d, int q, int bump, int bulk_ok)
 {
     extern __shared__ __align__(16) double pb_sm[];
+    __shared__ __align__(8) unsigned long long tma_bar;  // completion of the bulk copies of this CTA's slabs
     double *sr = pb_sm, *sc = pb_sm + PB_SLAB;
     int base;  // see pb_potf2_reg
     asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(base) : "l"(d_state + 1));
     const int panel = base + q;
     const i64 j0 = (i64)panel * PB_NB;
+    // everything that does not touch the predecessor's data comes before the wait: the tile, which of its slabs are whole (all
+    // NB x 64 entries inside the band and the matrix -- those arrive as 64 bulk copies of 512 contiguous bytes each, one per
+    // slab column ('U') or row ('L'), completing on an mbarrier), and the barrier's transaction count
+    const int tid = threadIdx.x;
+    const int nbl = (int)imin64_d(PB_NB, n - j0);
+    const i64 c1 = j0 + nbl;
+    const i64 ncols = imin64_d(kd, n - c1);
+    int tc = 0, rem = blockIdx.x;  // tile index -> (tr, tc), tr <= tc < ntile1d
+    while (rem > tc) { rem -= tc + 1; ++tc; }
+    const int tr = rem;
+    auto whole = [&](int tile) { return bulk_ok && nbl == PB_NB && (i64)tile * 64 + 64 <= ncols && tile * 64 + 127 <= kd; };
+    const bool bulk_r = whole(tr), bulk_c = tc != tr && whole(tc);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const unsigned bytes = ((bulk_r ? 1u : 0u) + (bulk_c ? 1u : 0u)) * (unsigned)(PB_NB * 64 * sizeof(double));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    }
+    __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (j0 >= n) return;
     int info0;
     asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(info0) : "l"(d_state) : "memory");
-    const int nbl = (int)imin64_d(PB_NB, n - j0);
     PB_STAMP(4, panel);
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the arrival counter of the panel kernel back to zero; the last panel of a replay
         d_state[3] = 0;                         // moves the base on for the next one
         if (bump) d_state[1] = base + bump;
     }
-    const i64 c1 = j0 + nbl;
-    const i64 ncols = imin64_d(kd, n - c1);
     if (ncols <= 0) return;
-    // tile index -> (tr, tc), tr <= tc < ntile1d
-    int tc = 0, rem = blockIdx.x;
-    while (rem > tc) { rem -= tc + 1; ++tc; }
-    const int tr = rem;
     if ((i64)tc * 64 >= ncols) return;
     double *p = p0;
-    const int tid = threadIdx.x;
     const int SI = (si == 1) ? 1 : 68, SX = (si == 1) ? PB_NB + 4 : 1;
     auto stage = [&](double *s, int tile) {
         for (int e = tid; e < PB_NB * 64; e += 256) {
@@ -581,8 +595,17 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict_
             cp_async8_zfill(s + i * SI + x * SX, p + (j0 + (ok ? i : 0)) * si + (ok ? k : j0) * sk, ok);
         }
     };
-    stage(sr, tr);
-    if (tc != tr) stage(sc, tc);
+    auto stage_bulk = [&](double *s, int tile, int c) {  // copy c of 64: slab column c ('U', si == 1) or slab row c ('L', sk == 1)
+        const double *src = p + j0 * si + (c1 + (i64)tile * 64) * sk + (i64)c * ((si == 1) ? sk : si);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s + c * (PB_NB + 4));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                     "r"((unsigned)(64 * sizeof(double))), "r"(bar)
+                     : "memory");
+    };
+    if (bulk_r) { if (tid < 64) stage_bulk(sr, tr, tid); } else stage(sr, tr);
+    if (tc != tr) {
+        if (bulk_c) { if (tid >= 64 && tid < 128) stage_bulk(sc, tc, tid - 64); } else stage(sc, tc);
+    }
     cp_async_commit();
     // accumulator layout of DMMA.8x8x4: lane holds C[row = lane/4][col = 2*(lane%4) + {0,1}] of each 8 x 8 tile
     const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
@@ -600,6 +623,12 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict_
             cv[t][q] = (rr <= cc && cc < ncols) ? p[(c1 + rr) * si + (c1 + cc) * sk] : 0.0;
         }
     cp_async_wait<0>();
+    if (bulk_r || bulk_c) {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
     __syncthreads();
     if (info0 != 0) return;  // the panel was not positive definite: nothing is written
     PB_STAMP(5, panel);
@@ -860,6 +889,9 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
     } else {
         const i64 npanels = cdiv64(n, PB_NB);
         const int ntile1d = (int)cdiv64(imin64(kd, n), 64);
+        // whole slabs of U12 reach shared memory as bulk copies (TMA) when their 512-byte pieces are 16-byte aligned: the pieces
+        // start at even element offsets (j0, c1 and the tile origin are multiples of 64) times the other stride
+        const int bulk_ok = (h->tune.pb_nobulk == 0 && ((uintptr_t)p0 % 16) == 0 && (((si == 1) ? sk : si) % 2) == 0) ? 1 : 0;
         const unsigned ntiles = (unsigned)(ntile1d * (ntile1d + 1) / 2);
         const unsigned trsm_blocks = (unsigned)cdiv64(imin64(kd, n) * PB_TPC, 256);
         const size_t smem3 = (size_t)2 * PB_SLAB * sizeof(double);
@@ -893,7 +925,7 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
             for (i64 q = 0; q < chunk && ce == cudaSuccess; ++q) {
                 cudaLaunchConfig_t c1c = cfg(trsm_blocks + 1, PB_K1T, 0), c3c = cfg(ntiles, 256, smem3);
                 ce = cudaLaunchKernelEx(&c1c, pb_potf2_reg, (i64)n, (int)kd, si, sk, p0, d_state, (int)q);
-                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c3c, pb_syrk, (i64)n, (int)kd, si, sk, p0, d_state, ntile1d, (int)q, (int)(q == chunk - 1 ? chunk : 0));
+                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c3c, pb_syrk, (i64)n, (int)kd, si, sk, p0, d_state, ntile1d, (int)q, (int)(q == chunk - 1 ? chunk : 0), bulk_ok);
             }
             const cudaError_t ee = cudaStreamEndCapture(gs, &graph);
             if (ce == cudaSuccess) ce = ee;

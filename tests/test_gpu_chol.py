@@ -111,6 +111,27 @@ def test_pbtrf_wide_blocked(bm, oracle_ob, rng, shape):
         assert np.max(np.abs(dB.cpu().numpy() - bref)) <= 1e-12 * max(1.0, np.max(np.abs(bref))), (uplo, n, kd)
 
 
+@pytest.mark.parametrize("shape", [(700, 128), (2000, 300), (3000, 1024), (4096, 64 * 3), (1000, 191)])
+def test_pbtrf_wide_bulk_staging_same_bits(bm, rng, shape):
+    """The update kernel stages whole slabs of U12 by bulk copies (TMA) when the band array's strides keep their 512-byte pieces
+    16-byte aligned, and by 8-byte cp.async otherwise (tuning pb_nobulk = 1 forces the latter): the arithmetic is the same, so
+    the factors must agree bit for bit, for both parities of the leading dimension."""
+    n, kd = shape
+    try:
+        for uplo, extra in itertools.product("UL", (0, 1)):
+            ab = _spd_band(rng, n, kd, uplo, extra)
+            out = []
+            for nobulk in (1, 0):
+                bm.handle(0).tune("pb_nobulk", nobulk)
+                dA = _dev(ab)
+                _, info = bm.pbtrf_(uplo, n, kd, dA)
+                assert info == 0
+                out.append(_host(dA))
+            assert np.array_equal(out[0], out[1]), (uplo, n, kd, extra)
+    finally:
+        bm.handle(0).tune("reset", 0)
+
+
 @pytest.mark.parametrize("kd", [3, 7, 20, 40, 100])
 def test_pbtrf_not_positive_definite(bm, oracle_c, rng, kd):
     n = 400
