@@ -259,17 +259,17 @@ __device__ unsigned long long pb_lastend[4][2];  // latest end over ALL CTAs of 
 #endif
 #define PB_TPC 16  // lanes per column of A12 in the substitution
 // Since the fusion with the former substitution kernel this kernel is launched with one CTA per 16 columns of A12: EVERY CTA factors the diagonal block
-// (redundantly -- the chain is the critical path anyway and the SMs are otherwise idle), keeps U11 in its shared memory and goes
-// straight on to the substitution for its own columns: one launch, one dependent global round trip and the staging of U11 less per
-// panel.  CTA 0 only factors and publishes: the factored block goes back into the matrix once every CTA of the grid has the
-// unfactored block in its registers (arrival counter d_state[3]; only CTA 0 ever waits, so CTAs of a grid larger than one wave
-// still get their turn), while the other CTAs are already substituting.
+// (redundantly -- the chain is the critical path anyway and the SMs are otherwise idle) and substitutes for its own columns row
+// group by row group INSIDE the factorisation loop, from the rows the factorisation posts in shared memory: one launch, one
+// dependent global round trip and the staging of U11 less per panel.  CTA 0 only factors and publishes: the factored block goes
+// back into the matrix once every CTA of the grid has the unfactored block in its registers (arrival counter d_state[3]; only
+// CTA 0 ever waits, so CTAs of a grid larger than one wave still get their turn).
 __global__ void __launch_bounds__(PB_K1T)
 pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, int q)
 {
-    __shared__ __align__(16) double u11[PB_NB * PB_NB];  // U11(i,t) at [i*NB + t] for t > i, else 0 (trsm phase)
-    __shared__ __align__(16) double xs[2][4][PB_NB];  // the four scaled rows of a row group, [row group parity][row][column]
-    __shared__ double rd[PB_NB + 1];
+    __shared__ __align__(16) double xs[4][4][PB_NB];  // the four scaled rows of a row group, [row group mod 4][row][column]: a ring of four,
+                                                      // because the substitution of a warp lags up to two row groups behind (below)
+    __shared__ __align__(16) double rd[PB_NB + 2];
     __shared__ __align__(16) double dpatch[16];        // the diagonal 4 x 4 patch of the current row group
     __shared__ int s_fail;
     // programmatic dependent launch (the three kernels of a panel are captured with it): this grid was launched while its
@@ -290,8 +290,6 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
     if (threadIdx.x == 0) s_fail = 0;
     PB_STAMP(0, s_panel);
     const int nbl = (int)imin64_d(PB_NB, n_total - j0);
-    if (nbl < PB_NB)  // a partial last panel: the substitution reads columns the factorisation never writes
-        for (int e = threadIdx.x; e < PB_NB * PB_NB; e += PB_K1T) u11[e] = 0.0;
     __syncthreads();
     double *p = p0 + j0 * (si + sk);  // U(j0, j0)
     // substitution phase, prepared now: CTA 0 only factors and publishes, CTA c >= 1 takes 16 columns of A12, 16 lanes per column,
@@ -335,6 +333,50 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
     asm volatile("mov.u32 %0, %0;" : "+r"(xr_a));
     asm volatile("mov.u32 %0, %0;" : "+r"(xc_a));
     int failed = 0;
+    // ---- substitution U12 = U11^{-T} A12 for this CTA's columns, one row group g (four rows) per call, INSIDE the factorisation
+    // loop: the rows of U11 it needs are the four scaled rows just posted in xs (with rd, the reciprocal diagonal), and every
+    // warp but the one on the critical path has slack until the next barrier.  Every lane runs the 4 x 4 forward substitution of
+    // the group on its own registers (only the owner's, lane g of the column's 16, is meaningful), the owner's four results go
+    // round by shuffles, the lanes below apply them to their four rows.  Per entry the subtractions come in ascending row order,
+    // one FMA each -- the order of the column-at-a-time substitution.  The warp that holds the next row group skips its turn
+    // (two iterations in a row) and catches up afterwards: hence the ring of four buffers.
+    const bool subst_cta = blockIdx.x > 0 && ncols12 > 0;
+    const unsigned tbase = (unsigned)lane & ~(unsigned)(PB_TPC - 1);
+    int sg = 0;  // next row group this warp substitutes (warp-uniform)
+    auto subst = [&](int g) {
+        const unsigned gb = xs0 + (unsigned)(g & 3) * (4u * PB_NB * 8u);
+        const unsigned dg = gb + (unsigned)g * 32u;  // row 0 of the buffer, column 4g
+        double ul[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            pb_lds2(gb + r * (PB_NB * 8u) + 32u * tq, ul[r][0], ul[r][1]);
+            pb_lds2(gb + r * (PB_NB * 8u) + 32u * tq + 16u, ul[r][2], ul[r][3]);
+        }
+        double d00, d01, d02, d03, d12, d13, d22, d23, r0, r1, r2, r3;
+        pb_lds2(dg, d00, d01);
+        pb_lds2(dg + 16u, d02, d03);
+        pb_lds2(dg + PB_NB * 8u + 16u, d12, d13);
+        pb_lds2(dg + 2u * PB_NB * 8u + 16u, d22, d23);
+        pb_lds2(rd0 + 32u * g, r0, r1);
+        pb_lds2(rd0 + 32u * g + 16u, r2, r3);
+        (void)d00; (void)d22;
+        const double x0 = __dmul_rn(ta[0], r0);
+        const double x1 = __dmul_rn(fma(-d01, x0, ta[1]), r1);
+        const double x2 = __dmul_rn(fma(-d12, x1, fma(-d02, x0, ta[2])), r2);
+        const double x3 = __dmul_rn(fma(-d23, x2, fma(-d13, x1, fma(-d03, x0, ta[3]))), r3);
+        const unsigned src = tbase + g;  // (posting the four results in shared memory instead of shuffling them measured the same)
+        const double b0 = __shfl_sync(0xffffffffu, x0, src), b1 = __shfl_sync(0xffffffffu, x1, src);
+        const double b2 = __shfl_sync(0xffffffffu, x2, src), b3 = __shfl_sync(0xffffffffu, x3, src);
+        if (tq == g) { ta[0] = x0; ta[1] = x1; ta[2] = x2; ta[3] = x3; }
+        if (tq > g) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double br = (r == 0) ? b0 : (r == 1) ? b1 : (r == 2) ? b2 : b3;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ta[c] = fma(-ul[r][c], br, ta[c]);
+            }
+        }
+    };
     if (info0 != 0) return;  // an earlier panel was not positive definite
 #pragma unroll 1
     for (int jb = 0; jb < PB_NB / 4 && 4 * jb < nbl; ++jb) {
@@ -346,7 +388,7 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
         // shuffled to every lane of the row-group warp (pipelined), every lane then factors D redundantly in registers -- four
         // rsqrt in sequence, no further communication -- and solves its own 4 x 4 patch of the row group against it (a 4 x 4
         // triangular substitution); the four scaled rows are posted and everyone below applies a rank-4 update.
-        const unsigned buf = (unsigned)(jb & 1) * (4u * PB_NB * 8u);  // double-buffered: the next row group posts while this one is read
+        const unsigned buf = (unsigned)(jb & 3) * (4u * PB_NB * 8u);  // ring of four: later row groups post while this one is still read
         if (inwarp) {
             // the diagonal patch goes through shared memory (one post, broadcast loads): shuffles issued by a single warp do not
             // pipeline (ten 64-bit shuffles cost ~300 cycles here)
@@ -438,6 +480,8 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
             }
         }
         if (nextwarp) asm volatile("bar.arrive 1, %0;" ::"n"(PB_K1T) : "memory");
+        if (subst_cta && !nextwarp)  // at most two groups per turn: a warp that owes three spreads them over two turns
+            for (int turn = 0; turn < 2 && sg <= jb; ++turn) subst(sg++);
     }
     __syncthreads();
     PB_STAMP(1, s_panel);
@@ -475,49 +519,10 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
         return;
     }
     if (ncols12 <= 0) return;
-    // the factor above the diagonal: into this CTA's shared memory for the substitution
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int r = 4 * a + u, c = 4 * b + w;
-            if (upper && r < c && c < nbl) u11[r * PB_NB + c] = v[u][w];
-        }
-    __syncthreads();
-    // ---- substitution U12 = U11^{-T} A12 for this CTA's columns, four rows (one row group g) per step: every lane runs the
-    // 4 x 4 forward substitution of the group on its own registers (only the owner's, lane g, is meaningful), the owner's four
-    // results are broadcast by shuffles, and the lanes below apply them to their four rows.  Per entry the subtractions come in
-    // ascending row order, each one FMA -- the order of the column-at-a-time substitution.
     {
-        const unsigned tbase = (unsigned)lane & ~(unsigned)(PB_TPC - 1);
-#pragma unroll
-        for (int g = 0; g < PB_NB / 4; ++g) {
-            const double *ug = u11 + (4 * g) * PB_NB;
-            const double d01 = ug[4 * g + 1], d02 = ug[4 * g + 2], d03 = ug[4 * g + 3];
-            const double d12 = ug[PB_NB + 4 * g + 2], d13 = ug[PB_NB + 4 * g + 3], d23 = ug[2 * PB_NB + 4 * g + 3];
-            const double r0 = (4 * g + 0 < nbl) ? rd[4 * g + 0] : 0.0, r1 = (4 * g + 1 < nbl) ? rd[4 * g + 1] : 0.0;
-            const double r2 = (4 * g + 2 < nbl) ? rd[4 * g + 2] : 0.0, r3 = (4 * g + 3 < nbl) ? rd[4 * g + 3] : 0.0;
-            const double x0 = __dmul_rn(ta[0], r0);
-            const double x1 = __dmul_rn(fma(-d01, x0, ta[1]), r1);
-            const double x2 = __dmul_rn(fma(-d12, x1, fma(-d02, x0, ta[2])), r2);
-            const double x3 = __dmul_rn(fma(-d23, x2, fma(-d13, x1, fma(-d03, x0, ta[3]))), r3);
-            const unsigned src = tbase + g;
-            const double b0 = __shfl_sync(0xffffffffu, x0, src), b1 = __shfl_sync(0xffffffffu, x1, src);
-            const double b2 = __shfl_sync(0xffffffffu, x2, src), b3 = __shfl_sync(0xffffffffu, x3, src);
-            if (tq == g) { ta[0] = x0; ta[1] = x1; ta[2] = x2; ta[3] = x3; }
-            if (tq > g) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const double2 ulo = *reinterpret_cast<const double2 *>(ug + r * PB_NB + 4 * tq);
-                    const double2 uhi = *reinterpret_cast<const double2 *>(ug + r * PB_NB + 4 * tq + 2);
-                    const double br = (r == 0) ? b0 : (r == 1) ? b1 : (r == 2) ? b2 : b3;
-                    ta[0] = fma(-ulo.x, br, ta[0]);
-                    ta[1] = fma(-ulo.y, br, ta[1]);
-                    ta[2] = fma(-uhi.x, br, ta[2]);
-                    ta[3] = fma(-uhi.y, br, ta[3]);
-                }
-            }
-        }
+        // the row groups this warp still owes (it was on the critical path at the end), then the result
+        const int ngroups = (nbl + 3) / 4;
+        while (sg < ngroups) subst(sg++);
 #pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
             const int i = 4 * tq + s2;
