@@ -48,6 +48,7 @@ struct bmb_tuning {
     int gbmv_spr = 0;          // > 0: systolic gbmv in short runs of this many 32-column sets, one per warp, non-persistent grid
     int pb_nodiag = 0;         // -1: narrow-band dpbtrf (kd <= 31) takes the one-warp register kernel instead of the window kernel
     int pb_nopdl = 0;          // 1 captures the blocked Cholesky without programmatic dependent launch
+    int pb_clate = 0;          // 1: the update kernel loads its C tile after the dependent-launch wait instead of before it
     int pb_nobulk = 0;         // 1: the blocked Cholesky's update kernel stages every slab by 8-byte cp.async (no bulk copies)
     int sbmv_rows_k = 16;      // band width below which dsbmv uses the row kernel
 };

@@ -210,7 +210,7 @@ extern "C" int bmb200_internal_set_tuning(bmb200_handle_t h, const char *key, lo
     bmb_tuning &t = h->tune;
     struct { const char *name; int *slot; } ints[] = {
         {"gbmm_ring", &t.gbmm_ring}, {"gbmm_nt", &t.gbmm_nt}, {"gbmm_rw", &t.gbmm_rw}, {"gbtrf_nopipe", &t.gbtrf_nopipe}, {"gbtrf_nostrip", &t.gbtrf_nostrip}, {"gbtrf_nomw", &t.gbtrf_nomw},
-        {"gbmm_wide", &t.gbmm_wide}, {"pb_nopdl", &t.pb_nopdl}, {"pb_nobulk", &t.pb_nobulk}, {"gbmv_spr", &t.gbmv_spr}, {"typed_nowin", &t.typed_nowin}, {"pb_nodiag", &t.pb_nodiag}, {"pipe_nospec", &t.pipe_nospec}, {"pipe_stats", &t.pipe_stats}, {"gbtrs_noblock", &t.gbtrs_noblock},
+        {"gbmm_wide", &t.gbmm_wide}, {"pb_nopdl", &t.pb_nopdl}, {"pb_nobulk", &t.pb_nobulk}, {"pb_clate", &t.pb_clate}, {"gbmv_spr", &t.gbmv_spr}, {"typed_nowin", &t.typed_nowin}, {"pb_nodiag", &t.pb_nodiag}, {"pipe_nospec", &t.pipe_nospec}, {"pipe_stats", &t.pipe_stats}, {"gbtrs_noblock", &t.gbtrs_noblock},
         {"gbtrs_pfdist_blocked", &t.gbtrs_pfdist_blocked}, {"gbtrs_nocluster", &t.gbtrs_nocluster}, {"gbtrs_nosplit", &t.gbtrs_nosplit},
         {"gbtrs_cluster", &t.gbtrs_cluster}, {"gbtrs_pfdist", &t.gbtrs_pfdist}, {"gbtrs_stats", &t.gbtrs_stats},
         {"debug", &t.debug}, {"sbmv_rows_k", &t.sbmv_rows_k},

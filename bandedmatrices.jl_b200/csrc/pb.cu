@@ -247,11 +247,11 @@ __device__ unsigned long long pb_lastend[4][2];  // latest end over ALL CTAs of 
             long long t_;                                                                           \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                  \
             pb_stamps[(panel) - 10][ev][blockIdx.x == 0 ? 0 : 1] = t_;                              \
-            if ((panel) == 13 && ev == 6 && blockIdx.x == 0)                                        \
-                for (int p_ = 0; p_ < 4; ++p_)                                                      \
-                    for (int e_ = 0; e_ < 7; ++e_)                                                  \
-                        printf("STAMP %d %d %lld %lld  last k1 %lld k3 %lld\n", p_ + 10, e_, pb_stamps[p_][e_][0] - pb_stamps[0][0][0], pb_stamps[p_][e_][1] - pb_stamps[0][0][0], (long long)pb_lastend[p_][0] - pb_stamps[0][0][0], (long long)pb_lastend[p_][1] - pb_stamps[0][0][0]); \
         }                                                                                           \
+        if (threadIdx.x == 0 && blockIdx.x == 0 && (panel) == 14 && ev == 4)                        \
+            for (int p_ = 0; p_ < 4; ++p_)                                                          \
+                for (int e_ = 0; e_ < 7; ++e_)                                                      \
+                    printf("STAMP %d %d %lld %lld  last k1 %lld k3 %lld\n", p_ + 10, e_, pb_stamps[p_][e_][0] - pb_stamps[0][0][0], pb_stamps[p_][e_][1] - pb_stamps[0][0][0], (long long)pb_lastend[p_][0] - pb_stamps[0][0][0], (long long)pb_lastend[p_][1] - pb_stamps[0][0][0]); \
     } while (0)
 #else
 #define PB_STAMP(what, panel) do { } while (0)
@@ -343,6 +343,7 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
     const bool subst_cta = blockIdx.x > 0 && ncols12 > 0;
     const unsigned tbase = (unsigned)lane & ~(unsigned)(PB_TPC - 1);
     int sg = 0;  // next row group this warp substitutes (warp-uniform)
+    bool arrived = false;
     auto subst = [&](int g) {
         const unsigned gb = xs0 + (unsigned)(g & 3) * (4u * PB_NB * 8u);
         const unsigned dg = gb + (unsigned)g * 32u;  // row 0 of the buffer, column 4g
@@ -454,6 +455,10 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
             }
         }
         __syncthreads();
+        if (jb == 1 && tid == 0) {  // every thread has used what it loaded from the block (iteration 0): CTA 0 may overwrite it
+            atomicAdd(&d_state[3], 1);
+            arrived = true;
+        }
         {
             int f;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(fl0));
@@ -485,7 +490,7 @@ pb_potf2_reg(i64 n_total, int kd, i64 si, i64 sk, double *__restrict__ p0, int *
     }
     __syncthreads();
     PB_STAMP(1, s_panel);
-    if (tid == 0) atomicAdd(&d_state[3], 1);  // every value loaded from the block has been consumed: CTA 0 may overwrite it
+    if (tid == 0 && !arrived) atomicAdd(&d_state[3], 1);  // a one-iteration panel, or an exit from iteration 0
     if (!failed) {
         int f;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(f) : "r"(fl0));
@@ -547,7 +552,7 @@ __device__ __forceinline__ void pb_dmma884(double &d0, double &d1, double a, dou
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __global__ void __launch_bounds__(256)
-pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, int ntile1d, int q, int bump, int bulk_ok)
+pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict__ d_state, int ntile1d, int q, int bump, int bulk_ok, int c_early)
 {
     extern __shared__ __align__(16) double pb_sm[];
     __shared__ __align__(8) unsigned long long tma_bar;  // completion of the bulk copies of this CTA's slabs
@@ -577,12 +582,28 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict_
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     }
     __syncthreads();
+    // the C tile too: the window was last written by the update kernel of the PREVIOUS panel, which had completed before the
+    // panel kernel this grid waits for could pass its own wait -- the panel kernel itself writes rows j0 .. j0+NB-1 only
+    const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    const i64 rr = (i64)tr * 64 + warp * 8 + lr;  // this lane's window row (accumulator layout of DMMA.8x8x4, below)
+    double cv[8][2];
+    auto load_c = [&]() {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {
+                const i64 cc = (i64)tc * 64 + t * 8 + 2 * lc + q2;
+                cv[t][q2] = (j0 < n && rr <= cc && cc < ncols) ? p0[(c1 + rr) * si + (c1 + cc) * sk] : 0.0;
+            }
+    };
+    if (c_early) load_c();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (j0 >= n) return;
     int info0;
     asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(info0) : "l"(d_state) : "memory");
     PB_STAMP(4, panel);
+    if (!c_early) load_c();
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the arrival counter of the panel kernel back to zero; the last panel of a replay
         d_state[3] = 0;                         // moves the base on for the next one
         if (bump) d_state[1] = base + bump;
@@ -613,20 +634,9 @@ pb_syrk(i64 n, int kd, i64 si, i64 sk, double *__restrict__ p0, int *__restrict_
     }
     cp_async_commit();
     // accumulator layout of DMMA.8x8x4: lane holds C[row = lane/4][col = 2*(lane%4) + {0,1}] of each 8 x 8 tile
-    const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
-    const i64 rr = (i64)tr * 64 + warp * 8 + lr;  // this lane's window row
     double acc[8][2];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-    // the C tile does not depend on the staged slabs: its loads overlap the copies
-    double cv[8][2];
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const i64 cc = (i64)tc * 64 + t * 8 + 2 * lc + q;
-            cv[t][q] = (rr <= cc && cc < ncols) ? p[(c1 + rr) * si + (c1 + cc) * sk] : 0.0;
-        }
     cp_async_wait<0>();
     if (bulk_r || bulk_c) {
         unsigned done = 0;
@@ -930,7 +940,7 @@ extern "C" int bmb200_dpbtrf(bmb200_handle_t h, char uplo, int64_t n, int64_t kd
             for (i64 q = 0; q < chunk && ce == cudaSuccess; ++q) {
                 cudaLaunchConfig_t c1c = cfg(trsm_blocks + 1, PB_K1T, 0), c3c = cfg(ntiles, 256, smem3);
                 ce = cudaLaunchKernelEx(&c1c, pb_potf2_reg, (i64)n, (int)kd, si, sk, p0, d_state, (int)q);
-                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c3c, pb_syrk, (i64)n, (int)kd, si, sk, p0, d_state, ntile1d, (int)q, (int)(q == chunk - 1 ? chunk : 0), bulk_ok);
+                if (ce == cudaSuccess) ce = cudaLaunchKernelEx(&c3c, pb_syrk, (i64)n, (int)kd, si, sk, p0, d_state, ntile1d, (int)q, (int)(q == chunk - 1 ? chunk : 0), bulk_ok, (int)(h->tune.pb_clate ? 0 : 1));
             }
             const cudaError_t ee = cudaStreamEndCapture(gs, &graph);
             if (ce == cudaSuccess) ce = ee;

@@ -11,11 +11,14 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 kd = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 uplo = sys.argv[3] if len(sys.argv) > 3 else "U"
 nrhs = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+for kv in sys.argv[5:]:  # tuning knobs of the handle, key=value (csrc/common.cuh bmb_tuning)
+    key, val = kv.split("=")
+    bm.handle(0).tune(key, int(val))
 g = torch.Generator(device="cuda").manual_seed(1)
 d0 = torch.rand((n, kd + 1), dtype=torch.float64, device="cuda", generator=g) - 0.5
 d0[:, kd if uplo == "U" else 0] = 2.0 * (kd + 1)
 best = 1e30
-for it in range(3):
+for it in range(5):
     d = d0.clone()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
